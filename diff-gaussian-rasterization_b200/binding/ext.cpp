@@ -1,0 +1,11 @@
+// ext.cpp — pybind11 module `_C` exporting the same three functions as the reference
+// (diff-gaussian-rasterization-{light,full}/ext.cpp:15-19).
+#include <torch/extension.h>
+
+#include "rasterize_points.h"
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
+  m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+  m.def("mark_visible", &markVisible);
+}

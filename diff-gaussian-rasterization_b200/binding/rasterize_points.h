@@ -1,0 +1,72 @@
+// rasterize_points.h — torch-facing entry points of the `_C` extension module.
+//
+// Same three exported operations, argument order and return tuples as the reference binding
+// (diff-gaussian-rasterization-light/rasterize_points.h:18-76 with -DGSR_VARIANT_LIGHT,
+//  diff-gaussian-rasterization-full/rasterize_points.h:18-72 with -DGSR_VARIANT_FULL); the
+// bodies only allocate tensors and hand raw pointers to libgsr_b200.so (include/gsr_b200.h).
+#pragma once
+#include <torch/extension.h>
+
+#include <tuple>
+
+#if defined(GSR_VARIANT_LIGHT)
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
+                       const torch::Tensor& colors, const torch::Tensor& opacity,
+                       const torch::Tensor& scales, const torch::Tensor& rotations,
+                       const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                       const torch::Tensor& viewmatrix, const torch::Tensor& gt_depth,
+                       const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                       const int image_height, const int image_width, const torch::Tensor& sh,
+                       const int degree, const torch::Tensor& campos, const bool prefiltered,
+                       const bool debug);
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+    const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_median_depth, const torch::Tensor& dL_dout_depth_var,
+    const torch::Tensor& gt_depth, const torch::Tensor& sh, const int degree,
+    const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+    const torch::Tensor& alphas, const bool debug, const torch::Tensor& perspec_matrix,
+    const bool track_off, const bool map_off);
+
+#elif defined(GSR_VARIANT_FULL)
+
+std::tuple<int, int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor>
+RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
+                       const torch::Tensor& colors, const torch::Tensor& opacity,
+                       const torch::Tensor& scales, const torch::Tensor& rotations,
+                       const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                       const torch::Tensor& viewmatrix, const torch::Tensor& gt_depth,
+                       const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                       const int image_height, const int image_width, const torch::Tensor& sh,
+                       const int degree, const torch::Tensor& campos, const bool prefiltered);
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+    const torch::Tensor& gt_depth, const torch::Tensor& projmatrix, const float tan_fovx,
+    const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_uncertainty, const torch::Tensor& sh, const int degree,
+    const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const int NG,
+    const torch::Tensor& perspec_matrix);
+
+#else
+#error "define GSR_VARIANT_LIGHT or GSR_VARIANT_FULL"
+#endif
+
+torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,
+                          torch::Tensor& projmatrix);

@@ -1,0 +1,245 @@
+// gsr_common.cuh — shared configuration, buffer layouts and device math for the B200-native
+// Gaussian-splat rasterizer core.  No GLM: 3x3 helpers below are column-major like the
+// reference's glm::mat3 so that floating-point association matches
+// (reference: cuda_rasterizer/forward.cu:74-152, auxiliary.h:41-164).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+// ---- compile-time configuration (reference: cuda_rasterizer/config.h:15-17) ------------------
+constexpr int kChannels = 3;
+constexpr int kTileX = 16;
+constexpr int kTileY = 16;
+constexpr int kTileThreads = kTileX * kTileY;  // one thread per pixel
+constexpr float kAlphaMin = 15.0f / 255.0f;    // reference forward.cu:360 (Inria uses 1/255)
+constexpr float kAlphaMax = 0.99f;
+constexpr float kTmin = 0.0001f;
+constexpr int kAccStride = 16;                 // floats per Gaussian in the backward accumulator
+
+enum Variant { kLight = 0, kFull = 1 };
+
+// accumulator slots (per Gaussian, written by the backward blend kernel with warp-reduced
+// atomics, consumed by the per-Gaussian backward kernel)
+enum AccSlot {
+  ACC_MX = 0, ACC_MY = 1,         // dL/dmean2D
+  ACC_CA = 2, ACC_CB = 3, ACC_CC = 4,  // dL/dconic (.x .y .w of the reference's float4)
+  ACC_OP = 5,                     // dL/dopacity
+  ACC_R = 6, ACC_G = 7, ACC_B = 8,  // dL/dcolor (sum alpha*T*dL/dpixel)
+  ACC_DEPTH = 9,                  // dL/ddepth (incl. the (depth-gt)^2 term)
+  ACC_PGX = 10, ACC_PGY = 11,     // pose: dL/d(ndc) as the reference's pose pass sees it (full)
+  ACC_PD = 12,                    // pose: sum alpha*T*dL/dD (light: all pairs; full: front-most)
+  ACC_MED = 13                    // light: sum of dL/dmedian over pixels that picked this Gaussian
+};
+
+// ---- option flags --------------------------------------------------------------------------
+struct Options {
+  int exact_ng;
+  int tight_tiles;
+};
+Options& options();
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define GSR_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      gsr::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                  \
+                     cudaGetErrorString(_e));                                              \
+      return GSR_E_CUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+#define GSR_LAUNCH_OK(debug, stream)                                                       \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream);                  \
+    if (_e != cudaSuccess) {                                                               \
+      gsr::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,              \
+                     cudaGetErrorString(_e));                                              \
+      return GSR_E_CUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+// ---- private buffer layouts ----------------------------------------------------------------
+// Every array starts on a 256-byte boundary inside the caller-provided chunk.
+struct Carver {
+  char* p;
+  size_t used;
+  explicit Carver(char* base) : p(base), used(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    used = (used + 255) & ~size_t(255);
+    T* r = p ? reinterpret_cast<T*>(p + used) : nullptr;
+    used += count * sizeof(T);
+    return r;
+  }
+};
+
+// Per-Gaussian state produced by preprocess_fwd and read by binning / blend / backward.
+struct GeomState {
+  float4* rec;             // [3P] packed blend record:
+                           //   rec[3i+0] = (x_pix, y_pix, conic.a, conic.b)
+                           //   rec[3i+1] = (conic.c, opacity, power_cut, depth)
+                           //   rec[3i+2] = (r, g, b, 0)
+  float* cov3D;            // [6P] (only when computed from scale/rotation)
+  unsigned char* clamped;  // [P] bit k set <=> colour channel k clamped at 0
+  uint32_t* tiles_touched; // [P]
+  uint32_t* offsets;       // [P] inclusive scan of tiles_touched
+  uint32_t* counters;      // [8]  0: num_rendered, 1: num_related
+  char* scan_temp;
+  size_t scan_bytes;
+  static size_t carve(GeomState& s, char* base, int P, size_t scan_bytes);
+};
+
+struct BinState {
+  uint64_t* keys_unsorted;  // [N]
+  uint64_t* keys;           // [N]
+  uint32_t* vals_unsorted;  // [N]
+  uint32_t* vals;           // [N] sorted Gaussian index per (tile, depth) entry
+  char* sort_temp;
+  size_t sort_bytes;
+  static size_t carve(BinState& s, char* base, size_t N, size_t sort_bytes);
+};
+
+struct ImgState {
+  uint2* ranges;            // [tiles] [start, end) into BinState::vals
+  uint32_t* n_contrib;      // [HW] 1-based list position of the last blended entry
+  float* final_T;           // [HW] (full only)
+  uint32_t* first_contrib;  // [HW] 1-based list position of the first blended entry (full only)
+  uint32_t* tile_last;      // [tiles] max n_contrib over the tile's pixels
+  static size_t carve(ImgState& s, char* base, int HW, int tiles, int variant);
+};
+
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(size_t N, int end_bit);
+
+// ---- device math ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+struct M3 {  // column-major: c[col][row], same convention as glm::mat3
+  float c[3][3];
+};
+
+__device__ __forceinline__ M3 m3_mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int col = 0; col < 3; ++col)
+#pragma unroll
+    for (int row = 0; row < 3; ++row)
+      R.c[col][row] = A.c[0][row] * B.c[col][0] + A.c[1][row] * B.c[col][1] + A.c[2][row] * B.c[col][2];
+  return R;
+}
+
+__device__ __forceinline__ M3 m3_transpose(const M3& A) {
+  M3 R;
+#pragma unroll
+  for (int col = 0; col < 3; ++col)
+#pragma unroll
+    for (int row = 0; row < 3; ++row) R.c[col][row] = A.c[row][col];
+  return R;
+}
+
+__device__ __forceinline__ float3 xform_point_4x3(const float3& p, const float* m) {
+  return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+                     m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+
+__device__ __forceinline__ float4 xform_point_4x4(const float3& p, const float* m) {
+  return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+                     m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+                     m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+
+// ndc -> pixel; the reference evaluates this in double (auxiliary.h:41-44) and rounds once.
+__device__ __forceinline__ float ndc_to_pix(float v, int S) {
+  return (float)((((double)v + 1.0) * (double)S - 1.0) * 0.5);
+}
+
+// Tile rectangle of a splat (auxiliary.h:46-56).
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy,
+                                          uint2& rmin, uint2& rmax) {
+  const float r = (float)radius;
+  rmin.x = (unsigned)min(gx, max(0, (int)((px - r) / (float)kTileX)));
+  rmin.y = (unsigned)min(gy, max(0, (int)((py - r) / (float)kTileY)));
+  rmax.x = (unsigned)min(gx, max(0, (int)((px + r + (float)(kTileX - 1)) / (float)kTileX)));
+  rmax.y = (unsigned)min(gy, max(0, (int)((py + r + (float)(kTileY - 1)) / (float)kTileY)));
+}
+
+// Spherical-harmonics constants (real SH basis up to degree 3, standard values).
+__device__ constexpr float kSH0 = 0.28209479177387814f;
+__device__ constexpr float kSH1 = 0.4886025119029199f;
+__device__ constexpr float kSH2[5] = {1.0925484305920792f, -1.0925484305920792f,
+                                      0.31539156525252005f, -1.0925484305920792f,
+                                      0.5462742152960396f};
+__device__ constexpr float kSH3[7] = {-0.5900435899266435f, 2.890611442640554f,
+                                      -0.4570457994644658f, 0.3731763325901154f,
+                                      -0.4570457994644658f, 1.445305721320277f,
+                                      -0.5900435899266435f};
+
+#endif  // __CUDACC__
+
+// ---- stage launchers (each file implements its kernels + launcher) ---------------------------
+struct Camera {
+  const float* view;   // [16] device
+  const float* proj;   // [16] device
+  const float* campos; // [3]  device
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  int W, H, grid_x, grid_y;
+};
+
+int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float* scales,
+                          float scale_modifier, const float* rotations, const float* opacities,
+                          const float* shs, const float* cov3D_precomp,
+                          const float* colors_precomp, const Camera& cam, int* radii,
+                          GeomState& g, bool prefiltered, bool debug, cudaStream_t stream);
+
+int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_alloc_fn alloc,
+                void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
+                cudaStream_t stream);
+
+int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinState& b,
+                            ImgState& img, const float* bg, const float* gt_depth,
+                            float* out_color, float* out_depth, float* out_median, float* out_alpha,
+                            float* out_var, float* gau_unc, int* gau_px, bool debug,
+                            cudaStream_t stream);
+
+int launch_render_fwd_full(const Camera& cam, const GeomState& g, const BinState& b,
+                           ImgState& img, const float* bg, float* out_color, float* out_depth,
+                           float* out_unc, bool count_related, bool debug, cudaStream_t stream);
+
+struct BlendGrads {       // per-pixel cotangents
+  const float* dL_dpix;   // [3,H,W]
+  const float* dL_ddepth; // [H,W]
+  const float* dL_dmedian;// [H,W] light
+  const float* dL_dvar;   // [H,W] light: depth_var, full: uncertainty
+};
+
+int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
+                      const ImgState& img, const float* bg, const float* gt_depth,
+                      const float* alphas /*light*/, const BlendGrads& cot, float* acc,
+                      bool debug, cudaStream_t stream);
+
+struct GaussGradOut {
+  float* dL_dmean2D; float* dL_dconic; float* dL_dopacity; float* dL_dcolor; float* dL_ddepth;
+  float* dL_dmean3D; float* dL_dcov3D; float* dL_dsh; float* dL_dscale; float* dL_drot;
+  float* dL_dview;
+};
+
+int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D,
+                          const int* radii, const float* shs, const float* scales,
+                          const float* rotations, float scale_modifier,
+                          const float* cov3D_precomp, const Camera& cam, const float* perspec,
+                          const GeomState& g, const float* acc, float* pose_partials,
+                          const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
+                          cudaStream_t stream);
+
+}  // namespace gsr

@@ -1,0 +1,524 @@
+// preprocess_bwd.cu — per-Gaussian backward stage (one thread per Gaussian), fusing what the
+// reference runs as separate kernels:
+//   computeCov2DCUDA        (light backward.cu:144-276, full backward.cu:174-387)
+//   BACKWARD::preprocessCUDA (light :348-416, full :459-537) incl. SH backward (:20-139 / :20-169)
+//                            and scale/rotation backward (:280-343 / :391-454)
+//   pose_gradient_preCUDA   (light :701-751) and the per-Gaussian half of ComputePG (full :990-1072)
+// Inputs are the per-Gaussian accumulator records written by render_bwd (16 floats each).
+// Every output element is written (zeros for culled Gaussians), so no memset pass is needed.
+// The 12 live entries of dL/dviewmatrix are reduced per block and written to `pose_partials`;
+// a second tiny kernel adds the partials in a fixed order (deterministic, no atomics).
+//
+// Roofline: HBM.  Algorithmic bytes per Gaussian: 64 (acc) + 44 + 12*M (inputs) + 24 (cov3D)
+// in, 12*M + 4*(3+3+4+1+3+1+3+6+3+4) out  ->  ~ 640 B at M = 16.
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr int kBwdThreads = 128;
+
+__device__ __forceinline__ float3 ld3(const float* p, int idx) {
+  return make_float3(p[3 * idx], p[3 * idx + 1], p[3 * idx + 2]);
+}
+__device__ __forceinline__ void st3(float* p, int idx, float a, float b, float c) {
+  if (p) { p[3 * idx] = a; p[3 * idx + 1] = b; p[3 * idx + 2] = c; }
+}
+
+// d(dir/|dir|)/d(dir) applied to dv (auxiliary.h:100-111)
+__device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
+  const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+  const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+  float3 r;
+  r.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+  r.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+  r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+  return r;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kBwdThreads)
+preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
+                      const int* __restrict__ radii, const float* __restrict__ shs,
+                      const unsigned char* __restrict__ clamped, const float* __restrict__ scales,
+                      const float* __restrict__ rotations, float scale_modifier,
+                      const float* __restrict__ cov3Ds, const float* __restrict__ view,
+                      const float* __restrict__ proj, const float* __restrict__ campos_p,
+                      const float* __restrict__ perspec, float fx, float fy, float tanx, float tany,
+                      const float* __restrict__ acc, float* __restrict__ pose_partials,
+                      GaussGradOut out, bool want_gauss, bool want_pose) {
+  extern __shared__ float sh_smem[];  // [kBwdThreads][M*3+1] SH in, dL/dSH out
+  __shared__ float s_pose[kBwdThreads / 32][12];
+  const int base = blockIdx.x * kBwdThreads;
+  const int idx = base + threadIdx.x;
+  const int row = M * 3 + 1;
+  const bool use_sh = (shs != nullptr) && want_gauss;
+  const int nvalid = min(kBwdThreads, P - base);
+  const int nfloats = nvalid * M * 3;
+
+  if (use_sh) {
+    const float* src = shs + (size_t)base * M * 3;
+    const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (nfloats >> 2) : 0;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (int v = threadIdx.x; v < nvec; v += kBwdThreads) {
+      const float4 q = __ldg(src4 + v);
+      const int f = v << 2;
+      const float vals[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ff = f + k;
+        const int g = ff / (M * 3);
+        sh_smem[g * row + (ff - g * M * 3)] = vals[k];
+      }
+    }
+    for (int ff = (nvec << 2) + threadIdx.x; ff < nfloats; ff += kBwdThreads) {
+      const int g = ff / (M * 3);
+      sh_smem[g * row + (ff - g * M * 3)] = __ldg(src + ff);
+    }
+    __syncthreads();
+  }
+
+  float pose[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) pose[k] = 0.f;
+
+  const bool live = idx < P && radii[idx] > 0;
+  float* my_sh = sh_smem + threadIdx.x * row;
+
+  if (idx < P && !live && want_gauss) {
+    st3(out.dL_dmean2D, idx, 0.f, 0.f, 0.f);
+    if (out.dL_dconic) {
+      reinterpret_cast<float4*>(out.dL_dconic)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (out.dL_dopacity) out.dL_dopacity[idx] = 0.f;
+    st3(out.dL_dcolor, idx, 0.f, 0.f, 0.f);
+    if (out.dL_ddepth) out.dL_ddepth[idx] = 0.f;
+    st3(out.dL_dmean3D, idx, 0.f, 0.f, 0.f);
+    if (out.dL_dcov3D) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) out.dL_dcov3D[(size_t)idx * 6 + k] = 0.f;
+    }
+    st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
+    if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_sh) {
+      for (int k = 0; k < M * 3; ++k) my_sh[k] = 0.f;
+    }
+  }
+
+  if (live) {
+    const float4* a4 = reinterpret_cast<const float4*>(acc + (size_t)idx * kAccStride);
+    const float4 a0 = a4[0], a1 = a4[1], a2 = a4[2], a3 = a4[3];
+    const float g_mx = a0.x, g_my = a0.y, g_ca = a0.z, g_cb = a0.w;
+    const float g_cc = a1.x, g_op = a1.y, g_r = a1.z, g_g = a1.w;
+    const float g_b = a2.x, g_depth = a2.y, g_pgx = a2.z, g_pgy = a2.w;
+    const float g_pd = a3.x, g_med = a3.y;
+
+    const float3 m = ld3(means3D, idx);
+    const float4 m_hom = xform_point_4x4(m, proj);
+    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+    float3 dq = make_float3(0.f, 0.f, 0.f);  // dRGB.dL/dcolor contracted with d(rgb)/d(campos)
+
+    if (want_gauss) {
+      // ---------------- 2D covariance / conic backward ----------------
+      const float* cov3D = cov3Ds + (size_t)idx * 6;
+      float3 t = xform_point_4x3(m, view);
+      const float limx = 1.3f * tanx, limy = 1.3f * tany;
+      const float txtz = t.x / t.z, tytz = t.y / t.z;
+      t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+      t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+      const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+      const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+
+      M3 J;
+      J.c[0][0] = fx / t.z; J.c[0][1] = 0.0f;     J.c[0][2] = -(fx * t.x) / (t.z * t.z);
+      J.c[1][0] = 0.0f;     J.c[1][1] = fy / t.z; J.c[1][2] = -(fy * t.y) / (t.z * t.z);
+      J.c[2][0] = 0.0f;     J.c[2][1] = 0.0f;     J.c[2][2] = 0.0f;
+      M3 Wm;
+      Wm.c[0][0] = view[0]; Wm.c[0][1] = view[4]; Wm.c[0][2] = view[8];
+      Wm.c[1][0] = view[1]; Wm.c[1][1] = view[5]; Wm.c[1][2] = view[9];
+      Wm.c[2][0] = view[2]; Wm.c[2][1] = view[6]; Wm.c[2][2] = view[10];
+      M3 V;
+      V.c[0][0] = cov3D[0]; V.c[0][1] = cov3D[1]; V.c[0][2] = cov3D[2];
+      V.c[1][0] = cov3D[1]; V.c[1][1] = cov3D[3]; V.c[1][2] = cov3D[4];
+      V.c[2][0] = cov3D[2]; V.c[2][1] = cov3D[4]; V.c[2][2] = cov3D[5];
+      const M3 T = m3_mul(Wm, J);
+      M3 cov2D = m3_mul(m3_mul(m3_transpose(T), m3_transpose(V)), T);
+      const float a = (cov2D.c[0][0] += 0.3f);
+      const float b = cov2D.c[0][1];
+      const float c = (cov2D.c[1][1] += 0.3f);
+      const float denom = a * c - b * b;
+      float dL_da = 0, dL_db = 0, dL_dc = 0;
+      const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+      float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* u = T.c[0];  // first column of T
+      const float* w = T.c[1];  // second column of T
+      if (denom2inv != 0) {
+        dL_da = denom2inv * (-c * c * g_ca + 2 * b * c * g_cb + (denom - a * c) * g_cc);
+        dL_dc = denom2inv * (-a * a * g_cc + 2 * a * b * g_cb + (denom - a * c) * g_ca);
+        dL_db = denom2inv * 2 * (b * c * g_ca - (denom + 2 * b * b) * g_cb + a * b * g_cc);
+        dcov[0] = (u[0] * u[0] * dL_da + u[0] * w[0] * dL_db + w[0] * w[0] * dL_dc);
+        dcov[3] = (u[1] * u[1] * dL_da + u[1] * w[1] * dL_db + w[1] * w[1] * dL_dc);
+        dcov[5] = (u[2] * u[2] * dL_da + u[2] * w[2] * dL_db + w[2] * w[2] * dL_dc);
+        dcov[1] = 2 * u[0] * u[1] * dL_da + (u[0] * w[1] + u[1] * w[0]) * dL_db + 2 * w[0] * w[1] * dL_dc;
+        dcov[2] = 2 * u[0] * u[2] * dL_da + (u[0] * w[2] + u[2] * w[0]) * dL_db + 2 * w[0] * w[2] * dL_dc;
+        dcov[4] = 2 * u[2] * u[1] * dL_da + (u[1] * w[2] + u[2] * w[1]) * dL_db + 2 * w[1] * w[2] * dL_dc;
+      }
+      if (out.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
+      }
+      // gradients w.r.t. the upper 2x3 block of T, then J, then the view-space mean t
+      float uV[3], wV[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        uV[k] = u[0] * V.c[k][0] + u[1] * V.c[k][1] + u[2] * V.c[k][2];
+        wV[k] = w[0] * V.c[k][0] + w[1] * V.c[k][1] + w[2] * V.c[k][2];
+      }
+      float dT0[3], dT1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        dT0[k] = 2 * uV[k] * dL_da + wV[k] * dL_db;
+        dT1[k] = 2 * wV[k] * dL_dc + uV[k] * dL_db;
+      }
+      const float dL_dJ00 = Wm.c[0][0] * dT0[0] + Wm.c[0][1] * dT0[1] + Wm.c[0][2] * dT0[2];
+      const float dL_dJ02 = Wm.c[2][0] * dT0[0] + Wm.c[2][1] * dT0[1] + Wm.c[2][2] * dT0[2];
+      const float dL_dJ11 = Wm.c[1][0] * dT1[0] + Wm.c[1][1] * dT1[1] + Wm.c[1][2] * dT1[2];
+      const float dL_dJ12 = Wm.c[2][0] * dT1[0] + Wm.c[2][1] * dT1[1] + Wm.c[2][2] * dT1[2];
+      const float tz = 1.f / t.z;
+      const float tz2 = tz * tz;
+      const float tz3 = tz2 * tz;
+      const float dL_dtx = x_grad_mul * -fx * tz2 * dL_dJ02;
+      const float dL_dty = y_grad_mul * -fy * tz2 * dL_dJ12;
+      const float dL_dtz = -fx * tz2 * dL_dJ00 - fy * tz2 * dL_dJ11 + (2 * fx * t.x) * tz3 * dL_dJ02 +
+                           (2 * fy * t.y) * tz3 * dL_dJ12;
+      const float3 dmean_cov =
+          make_float3(view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz,
+                      view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
+                      view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz);
+
+      // ---------------- depth, median and screen-space mean terms ----------------
+      const float mul3 = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
+      const float3 dz = make_float3(view[2] - view[3] * mul3, view[6] - view[7] * mul3,
+                                    view[10] - view[11] * mul3);
+      const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
+      const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
+      float3 dmean_2d;
+      dmean_2d.x = (proj[0] * m_w - proj[3] * mul1) * g_mx + (proj[1] * m_w - proj[3] * mul2) * g_my;
+      dmean_2d.y = (proj[4] * m_w - proj[7] * mul1) * g_mx + (proj[5] * m_w - proj[7] * mul2) * g_my;
+      dmean_2d.z = (proj[8] * m_w - proj[11] * mul1) * g_mx + (proj[9] * m_w - proj[11] * mul2) * g_my;
+
+      float3 dmean;
+      if (VARIANT == kLight) {
+        // light: median atomics first, then += cov part, += 2D part, += depth part
+        dmean = make_float3(dz.x * g_med * 1.0f, dz.y * g_med * 1.0f, dz.z * g_med * 1.0f);
+        dmean.x += dmean_cov.x; dmean.y += dmean_cov.y; dmean.z += dmean_cov.z;
+        dmean.x += dmean_2d.x;  dmean.y += dmean_2d.y;  dmean.z += dmean_2d.z;
+        dmean.x += dz.x * g_depth; dmean.y += dz.y * g_depth; dmean.z += dz.z * g_depth;
+      } else {
+        // full: cov part (assigned) + depth part inside the cov2D kernel, then += 2D part
+        dmean = make_float3(dmean_cov.x + g_depth * dz.x, dmean_cov.y + g_depth * dz.y,
+                            dmean_cov.z + g_depth * dz.z);
+        dmean.x += dmean_2d.x;  dmean.y += dmean_2d.y;  dmean.z += dmean_2d.z;
+      }
+
+      // ---------------- SH backward ----------------
+      if (shs != nullptr) {
+        const float3 campos = make_float3(campos_p[0], campos_p[1], campos_p[2]);
+        const float3 dir_orig = make_float3(m.x - campos.x, m.y - campos.y, m.z - campos.z);
+        const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+        const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+        const unsigned char cb = clamped[idx];
+        const float dR[3] = {g_r * ((cb & 1) ? 0.f : 1.f), g_g * ((cb & 2) ? 0.f : 1.f),
+                             g_b * ((cb & 4) ? 0.f : 1.f)};
+        float dx_[3] = {0.f, 0.f, 0.f}, dy_[3] = {0.f, 0.f, 0.f}, dz_[3] = {0.f, 0.f, 0.f};
+        float coef[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) coef[k] = 0.f;
+        coef[0] = kSH0;
+#define SH(k, ch) my_sh[3 * (k) + (ch)]
+        if (D > 0) {
+          coef[1] = -kSH1 * y; coef[2] = kSH1 * z; coef[3] = -kSH1 * x;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            dx_[ch] = -kSH1 * SH(3, ch);
+            dy_[ch] = -kSH1 * SH(1, ch);
+            dz_[ch] = kSH1 * SH(2, ch);
+          }
+          if (D > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z;
+            const float xy = x * y, yz = y * z, xz = x * z;
+            coef[4] = kSH2[0] * xy; coef[5] = kSH2[1] * yz; coef[6] = kSH2[2] * (2.f * zz - xx - yy);
+            coef[7] = kSH2[3] * xz; coef[8] = kSH2[4] * (xx - yy);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              dx_[ch] += kSH2[0] * y * SH(4, ch) + kSH2[2] * 2.f * -x * SH(6, ch) + kSH2[3] * z * SH(7, ch) + kSH2[4] * 2.f * x * SH(8, ch);
+              dy_[ch] += kSH2[0] * x * SH(4, ch) + kSH2[1] * z * SH(5, ch) + kSH2[2] * 2.f * -y * SH(6, ch) + kSH2[4] * 2.f * -y * SH(8, ch);
+              dz_[ch] += kSH2[1] * y * SH(5, ch) + kSH2[2] * 2.f * 2.f * z * SH(6, ch) + kSH2[3] * x * SH(7, ch);
+            }
+            if (D > 2) {
+              coef[9] = kSH3[0] * y * (3.f * xx - yy);
+              coef[10] = kSH3[1] * xy * z;
+              coef[11] = kSH3[2] * y * (4.f * zz - xx - yy);
+              coef[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+              coef[13] = kSH3[4] * x * (4.f * zz - xx - yy);
+              coef[14] = kSH3[5] * z * (xx - yy);
+              coef[15] = kSH3[6] * x * (xx - 3.f * yy);
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                dx_[ch] += (kSH3[0] * SH(9, ch) * 3.f * 2.f * xy + kSH3[1] * SH(10, ch) * yz +
+                            kSH3[2] * SH(11, ch) * -2.f * xy + kSH3[3] * SH(12, ch) * -3.f * 2.f * xz +
+                            kSH3[4] * SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
+                            kSH3[5] * SH(14, ch) * 2.f * xz + kSH3[6] * SH(15, ch) * 3.f * (xx - yy));
+                dy_[ch] += (kSH3[0] * SH(9, ch) * 3.f * (xx - yy) + kSH3[1] * SH(10, ch) * xz +
+                            kSH3[2] * SH(11, ch) * (-3.f * yy + 4.f * zz - xx) +
+                            kSH3[3] * SH(12, ch) * -3.f * 2.f * yz + kSH3[4] * SH(13, ch) * -2.f * xy +
+                            kSH3[5] * SH(14, ch) * -2.f * yz + kSH3[6] * SH(15, ch) * -3.f * 2.f * xy);
+                dz_[ch] += (kSH3[1] * SH(10, ch) * xy + kSH3[2] * SH(11, ch) * 4.f * 2.f * yz +
+                            kSH3[3] * SH(12, ch) * 3.f * (2.f * zz - xx - yy) +
+                            kSH3[4] * SH(13, ch) * 4.f * 2.f * xz + kSH3[5] * SH(14, ch) * (xx - yy));
+              }
+            }
+          }
+        }
+#undef SH
+        const int ncoef = (D + 1) * (D + 1);
+        for (int k = 0; k < M; ++k) {
+          const float ck = (k < ncoef && k < 16) ? coef[k] : 0.f;
+          my_sh[3 * k + 0] = ck * dR[0];
+          my_sh[3 * k + 1] = ck * dR[1];
+          my_sh[3 * k + 2] = ck * dR[2];
+        }
+        const float3 dL_ddir = make_float3(dx_[0] * dR[0] + dx_[1] * dR[1] + dx_[2] * dR[2],
+                                           dy_[0] * dR[0] + dy_[1] * dR[1] + dy_[2] * dR[2],
+                                           dz_[0] * dR[0] + dz_[1] * dR[1] + dz_[2] * dR[2]);
+        const float3 dmean_sh = dnormvdv3(dir_orig, dL_ddir);
+        dmean.x += dmean_sh.x; dmean.y += dmean_sh.y; dmean.z += dmean_sh.z;
+
+        if (VARIANT == kFull) {
+          // d(rgb)/d(campos) = dRGB/d(dir) . d(dir)/d(campos) (full backward.cu:14-30,146-154),
+          // contracted with the UNclamped colour gradient sum alpha*T*dL/dpixel (ComputePG part 1)
+          const float len3 = len * len * len;
+          const float il3 = 1.0f / len3, il = 1.0f / len;
+          const float dxdCx = dir_orig.x * dir_orig.x * il3 - il;
+          const float dydCx = dir_orig.x * dir_orig.y * il3;
+          const float dzdCx = dir_orig.x * dir_orig.z * il3;
+          const float dxdCy = dir_orig.x * dir_orig.y * il3;
+          const float dydCy = dir_orig.y * dir_orig.y * il3 - il;
+          const float dzdCy = dir_orig.y * dir_orig.z * il3;
+          const float dxdCz = dir_orig.x * dir_orig.z * il3;
+          const float dydCz = dir_orig.y * dir_orig.z * il3;
+          const float dzdCz = dir_orig.z * dir_orig.z * il3 - il;
+          const float gc[3] = {g_r, g_g, g_b};
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            dq.x += gc[ch] * (dx_[ch] * dxdCx + dy_[ch] * dydCx + dz_[ch] * dzdCx);
+            dq.y += gc[ch] * (dx_[ch] * dxdCy + dy_[ch] * dydCy + dz_[ch] * dzdCy);
+            dq.z += gc[ch] * (dx_[ch] * dxdCz + dy_[ch] * dydCz + dz_[ch] * dzdCz);
+          }
+        }
+      }
+
+      // ---------------- scale / rotation backward ----------------
+      if (scales != nullptr) {
+        const float3 sc = ld3(scales, idx);
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        M3 R;
+        R.c[0][0] = 1.f - 2.f * (y * y + z * z); R.c[0][1] = 2.f * (x * y - r * z); R.c[0][2] = 2.f * (x * z + r * y);
+        R.c[1][0] = 2.f * (x * y + r * z); R.c[1][1] = 1.f - 2.f * (x * x + z * z); R.c[1][2] = 2.f * (y * z - r * x);
+        R.c[2][0] = 2.f * (x * z - r * y); R.c[2][1] = 2.f * (y * z + r * x); R.c[2][2] = 1.f - 2.f * (x * x + y * y);
+        const float3 s = make_float3(scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z);
+        M3 S;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) S.c[i][j] = (i == j) ? 1.0f : 0.0f;
+        S.c[0][0] = s.x; S.c[1][1] = s.y; S.c[2][2] = s.z;
+        const M3 Mm = m3_mul(S, R);
+        M3 dSig;
+        dSig.c[0][0] = dcov[0];        dSig.c[0][1] = 0.5f * dcov[1]; dSig.c[0][2] = 0.5f * dcov[2];
+        dSig.c[1][0] = 0.5f * dcov[1]; dSig.c[1][1] = dcov[3];        dSig.c[1][2] = 0.5f * dcov[4];
+        dSig.c[2][0] = 0.5f * dcov[2]; dSig.c[2][1] = 0.5f * dcov[4]; dSig.c[2][2] = dcov[5];
+        M3 M2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) M2.c[i][j] = 2.0f * Mm.c[i][j];
+        const M3 dL_dM = m3_mul(M2, dSig);
+        const M3 Rt = m3_transpose(R);
+        M3 dMt = m3_transpose(dL_dM);
+        const float dsx = Rt.c[0][0] * dMt.c[0][0] + Rt.c[0][1] * dMt.c[0][1] + Rt.c[0][2] * dMt.c[0][2];
+        const float dsy = Rt.c[1][0] * dMt.c[1][0] + Rt.c[1][1] * dMt.c[1][1] + Rt.c[1][2] * dMt.c[1][2];
+        const float dsz = Rt.c[2][0] * dMt.c[2][0] + Rt.c[2][1] * dMt.c[2][1] + Rt.c[2][2] * dMt.c[2][2];
+        st3(out.dL_dscale, idx, dsx, dsy, dsz);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          dMt.c[0][j] *= s.x;
+          dMt.c[1][j] *= s.y;
+          dMt.c[2][j] *= s.z;
+        }
+        float4 dq4;
+        dq4.x = 2 * z * (dMt.c[0][1] - dMt.c[1][0]) + 2 * y * (dMt.c[2][0] - dMt.c[0][2]) + 2 * x * (dMt.c[1][2] - dMt.c[2][1]);
+        dq4.y = 2 * y * (dMt.c[1][0] + dMt.c[0][1]) + 2 * z * (dMt.c[2][0] + dMt.c[0][2]) + 2 * r * (dMt.c[1][2] - dMt.c[2][1]) - 4 * x * (dMt.c[2][2] + dMt.c[1][1]);
+        dq4.z = 2 * x * (dMt.c[1][0] + dMt.c[0][1]) + 2 * r * (dMt.c[2][0] - dMt.c[0][2]) + 2 * z * (dMt.c[1][2] + dMt.c[2][1]) - 4 * y * (dMt.c[2][2] + dMt.c[0][0]);
+        dq4.w = 2 * r * (dMt.c[0][1] - dMt.c[1][0]) + 2 * x * (dMt.c[2][0] + dMt.c[0][2]) + 2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
+        if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = dq4;  // w.r.t. the raw quaternion
+      } else {
+        st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
+        if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+
+      st3(out.dL_dmean3D, idx, dmean.x, dmean.y, dmean.z);
+      st3(out.dL_dmean2D, idx, g_mx, g_my, 0.f);
+      if (out.dL_dconic) reinterpret_cast<float4*>(out.dL_dconic)[idx] = make_float4(g_ca, g_cb, 0.f, g_cc);
+      if (out.dL_dopacity) out.dL_dopacity[idx] = g_op;
+      st3(out.dL_dcolor, idx, g_r, g_g, g_b);
+      if (out.dL_ddepth) out.dL_ddepth[idx] = g_depth;
+    }
+
+    // ---------------- pose gradient, per-Gaussian contraction ----------------
+    if (want_pose) {
+      const float p0 = perspec[0], p5 = perspec[5];
+      const float gx = (VARIANT == kLight) ? g_mx : g_pgx;
+      const float gy = (VARIANT == kLight) ? g_my : g_pgy;
+      const float ax = m_w * p0;              // d x_ndc / d v{0,4,8,12}   = ax * (m,1)
+      const float by = m_w * p5;              // d y_ndc / d v{1,5,9,13}   = by * (m,1)
+      const float cx = m_hom.x * (-m_w * m_w);  // d x_ndc / d v{2,6,10,14} = cx * (m,1)
+      const float cy = m_hom.y * (-m_w * m_w);  // d y_ndc / d v{2,6,10,14} = cy * (m,1)
+      const float mm[4] = {m.x, m.y, m.z, 1.0f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pose[3 * k + 0] = (ax * mm[k]) * gx;
+        pose[3 * k + 1] = (by * mm[k]) * gy;
+        pose[3 * k + 2] = (cx * mm[k]) * gx + (cy * mm[k]) * gy + mm[k] * g_pd;
+      }
+      if (VARIANT == kFull) {
+        // colour through the camera position: campos = -R^T t, so
+        // d campos_x / d v{0,1,2} = -v{12,13,14}, ... , d campos / d v12 = -(v0,v4,v8) etc.
+        pose[0] += dq.x * (-view[12]); pose[1] += dq.x * (-view[13]); pose[2] += dq.x * (-view[14]);
+        pose[3] += dq.y * (-view[12]); pose[4] += dq.y * (-view[13]); pose[5] += dq.y * (-view[14]);
+        pose[6] += dq.z * (-view[12]); pose[7] += dq.z * (-view[13]); pose[8] += dq.z * (-view[14]);
+        pose[9] += dq.x * (-view[0]) + dq.y * (-view[4]) + dq.z * (-view[8]);
+        pose[10] += dq.x * (-view[1]) + dq.y * (-view[5]) + dq.z * (-view[9]);
+        pose[11] += dq.x * (-view[2]) + dq.y * (-view[6]) + dq.z * (-view[10]);
+      }
+    }
+  }
+
+  // coalesced store of the block's dL/dSH slab
+  if (use_sh && out.dL_dsh != nullptr) {
+    __syncthreads();
+    float* dst = out.dL_dsh + (size_t)base * M * 3;
+    const int nvec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (nfloats >> 2) : 0;
+    float4* dst4 = reinterpret_cast<float4*>(dst);
+    for (int v = threadIdx.x; v < nvec; v += kBwdThreads) {
+      float vals[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ff = (v << 2) + k;
+        const int g = ff / (M * 3);
+        vals[k] = sh_smem[g * row + (ff - g * M * 3)];
+      }
+      dst4[v] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    }
+    for (int ff = (nvec << 2) + threadIdx.x; ff < nfloats; ff += kBwdThreads) {
+      const int g = ff / (M * 3);
+      dst[ff] = sh_smem[g * row + (ff - g * M * 3)];
+    }
+  }
+
+  if (want_pose) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      float s = pose[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_pose[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      float s = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < kBwdThreads / 32; ++wq) s += s_pose[wq][threadIdx.x];
+      pose_partials[(size_t)blockIdx.x * 12 + threadIdx.x] = s;
+    }
+  }
+}
+
+// Adds the per-block pose partials in a fixed order and scatters the 12 live entries into the
+// 16-float column-major dL/dviewmatrix (entries 3,7,11,15 stay 0, as in the reference).
+__global__ void __launch_bounds__(384)
+pose_finalize_kernel(int nblocks, const float* __restrict__ partials, float* __restrict__ dL_dview,
+                     bool want_pose) {
+  __shared__ float s[32][12];
+  const int k = threadIdx.x % 12;
+  const int lane = threadIdx.x / 12;  // 32 strided accumulators per entry
+  float sum = 0.f;
+  if (want_pose)
+    for (int b = lane; b < nblocks; b += 32) sum += partials[(size_t)b * 12 + k];
+  s[lane][k] = sum;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float total = 0.f;
+    const int col = threadIdx.x >> 2, rowi = threadIdx.x & 3;  // flat index = 4*col + row
+    if (rowi < 3) {
+      const int kk = 3 * col + rowi;  // pose[] order: (v0,v1,v2),(v4,v5,v6),(v8,v9,v10),(v12,v13,v14)
+      for (int l = 0; l < 32; ++l) total += s[l][kk];
+    }
+    dL_dview[threadIdx.x] = total;
+  }
+}
+
+}  // namespace
+
+int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D,
+                          const int* radii, const float* shs, const float* scales,
+                          const float* rotations, float scale_modifier,
+                          const float* cov3D_precomp, const Camera& cam, const float* perspec,
+                          const GeomState& g, const float* acc, float* pose_partials,
+                          const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
+                          cudaStream_t stream) {
+  const int blocks = (P + kBwdThreads - 1) / kBwdThreads;
+  const size_t smem = (shs != nullptr && want_gauss) ? sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1) : 0;
+  const float* cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
+  if (!want_gauss) {
+    // light + map_off: every per-Gaussian gradient is zero (light backward.cu:593,609,654,666;
+    // rasterizer_impl.cu:467)
+    auto zero = [&](float* p, size_t n) -> cudaError_t {
+      return p ? cudaMemsetAsync(p, 0, n * sizeof(float), stream) : cudaSuccess;
+    };
+    GSR_CUDA_OK(zero(out.dL_dmean2D, 3 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dconic, 4 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dopacity, (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dcolor, 3 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_ddepth, (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dmean3D, 3 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dcov3D, 6 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dsh, 3 * (size_t)P * (size_t)M));
+    GSR_CUDA_OK(zero(out.dL_dscale, 3 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_drot, 4 * (size_t)P));
+  } else if (shs == nullptr && out.dL_dsh != nullptr && M > 0) {
+    GSR_CUDA_OK(cudaMemsetAsync(out.dL_dsh, 0, sizeof(float) * 3 * (size_t)P * (size_t)M, stream));
+  }
+  if (want_gauss || want_pose) {
+    if (variant == kLight) {
+      preprocess_bwd_kernel<kLight><<<blocks, kBwdThreads, smem, stream>>>(
+          P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D,
+          cam.view, cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx,
+          cam.tan_fovy, acc, pose_partials, out, want_gauss, want_pose);
+    } else {
+      preprocess_bwd_kernel<kFull><<<blocks, kBwdThreads, smem, stream>>>(
+          P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D,
+          cam.view, cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx,
+          cam.tan_fovy, acc, pose_partials, out, want_gauss, want_pose);
+    }
+    GSR_LAUNCH_OK(debug, stream);
+  }
+  pose_finalize_kernel<<<1, 384, 0, stream>>>(blocks, pose_partials, out.dL_dview, want_pose);
+  GSR_LAUNCH_OK(debug, stream);
+  return GSR_OK;
+}
+
+}  // namespace gsr

@@ -1,0 +1,179 @@
+/*
+ * gsr_b200.h — C ABI of the B200-native differentiable Gaussian-splat rasterizer core
+ * (libgsr_b200.so).
+ *
+ * This is the drop-in boundary of the hot path: the five operations below replace, one for
+ * one, the C++ statics of the reference's CUDA core that its torch binding calls
+ *
+ *   gsr_light_forward   <- CudaRasterizer::Rasterizer::forward   (light)
+ *                          diff-gaussian-rasterization-light/cuda_rasterizer/rasterizer.h:31-63
+ *   gsr_light_backward  <- CudaRasterizer::Rasterizer::backward  (light)  rasterizer.h:65-104
+ *   gsr_full_forward    <- CudaRasterizer::Rasterizer::forward   (full)
+ *                          diff-gaussian-rasterization-full/cuda_rasterizer/rasterizer.h:31-59
+ *   gsr_full_backward   <- CudaRasterizer::Rasterizer::backward  (full)   rasterizer.h:61-102
+ *   gsr_mark_visible    <- CudaRasterizer::Rasterizer::markVisible        rasterizer.h:24-29
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 / int32 data unless stated otherwise; "absent"
+ *    optional inputs (shs / colors_precomp, scales+rotations / cov3D_precomp) are NULL, exactly
+ *    as the reference's kernels test them (forward.cu:205,241);
+ *  - 4x4 matrices are 16 floats read column-major (m[0],m[4],m[8],m[12] = row 0), i.e. callers
+ *    pass the transposed world-to-camera / full-projection matrices like Inria 3DGS does
+ *    (auxiliary.h:58-77);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *    enqueued on it.  The forward calls block once on that stream to read back the duplicate
+ *    count that sizes the binning buffer (the reference blocks in the same place,
+ *    rasterizer_impl.cu:287);
+ *  - the three opaque buffers (geometry / binning / image state) are obtained through C
+ *    allocator callbacks `char* (*)(void* ctx, size_t bytes)` which must return device memory
+ *    aligned to at least 256 bytes that stays valid until the matching backward has run
+ *    (the reference uses std::function<char*(size_t)> resize lambdas for the same purpose,
+ *    rasterize_points.cu:27-33).  Their internal layout is private to this library;
+ *  - outputs need not be pre-zeroed: every output element is written by the call;
+ *  - every entry point returns 0 on success and a negative GSR_E_* code on failure;
+ *    gsr_last_error() gives a thread-local human-readable message.
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+#define GSR_OK 0
+#define GSR_E_INVALID (-1)   /* bad argument (shape / null pointer / unsupported channel count) */
+#define GSR_E_CUDA (-2)      /* a CUDA runtime call or kernel failed */
+#define GSR_E_ALLOC (-3)     /* an allocator callback returned NULL */
+
+typedef char* (*gsr_alloc_fn)(void* ctx, size_t bytes);
+
+/* ABI version of the loaded library (== GSR_B200_ABI_VERSION it was built with). */
+GSR_API int gsr_abi_version(void);
+
+/* Thread-local message describing the last failure in this thread ("" if none). */
+GSR_API const char* gsr_last_error(void);
+
+/* Number of floats of caller-provided, uninitialised device scratch a backward call needs. */
+GSR_API size_t gsr_backward_scratch_floats(int P);
+
+/* Tuning switches (process-wide, not part of the reference surface).
+ *   "exact_ng"      1 (default): gsr_full_forward returns the exact number of valid
+ *                   (pixel, Gaussian) pairs like the reference; 0: skip the count + sync, return 0.
+ *   "tight_tiles"   1: drop (tile, Gaussian) duplicates that provably cannot reach the
+ *                   alpha >= 15/255 threshold inside the tile (outputs unchanged, num_rendered
+ *                   smaller than the reference's); 0 (default): the reference's rectangle rule.
+ * Returns the previous value, or GSR_E_INVALID for an unknown key. */
+GSR_API int gsr_set_option(const char* key, int value);
+GSR_API int gsr_get_option(const char* key);
+
+/* ---- light variant ---------------------------------------------------------------------- */
+
+/* replaces L/cuda_rasterizer/rasterizer.h:31-63  (Rasterizer::forward).
+ * out_color[3,H,W], out_depth/out_median_depth/out_alpha/out_depth_var[H,W], radii[P],
+ * gau_uncertainty[P], gau_related_pixels[P].  *num_rendered receives the number of
+ * (Gaussian, tile) duplicates (the int the reference returns). */
+GSR_API int gsr_light_forward(
+    gsr_alloc_fn geom_alloc, void* geom_ctx,
+    gsr_alloc_fn binning_alloc, void* binning_ctx,
+    gsr_alloc_fn img_alloc, void* img_ctx,
+    int P, int D, int M,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    float* out_color, float* out_depth, float* out_median_depth, float* out_alpha,
+    const float* gt_depth, float* out_depth_var,
+    float* gau_uncertainty, int* gau_related_pixels, int* radii,
+    int debug, void* stream, int* num_rendered);
+
+/* replaces L/cuda_rasterizer/rasterizer.h:65-104 (Rasterizer::backward).
+ * dL_dmean2D[P,3], dL_dconic[P,4], dL_dopacity[P], dL_dcolor[P,3], dL_ddepth[P],
+ * dL_dmean3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscale[P,3], dL_drot[P,4],
+ * dL_dview[16] (already summed over pixels; the reference returns [H*W,16] and sums in Python).
+ * `scratch` = gsr_backward_scratch_floats(P) floats. */
+GSR_API int gsr_light_backward(
+    int P, int D, int M, int R,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* alphas, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, const int* radii,
+    char* geom_buffer, char* binning_buffer, char* img_buffer,
+    const float* dL_dpix, const float* dL_dpix_depth,
+    const float* dL_dpix_median_depth, const float* dL_dpix_depth_var,
+    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+    float* dL_dscale, float* dL_drot,
+    int debug, const float* perspec_matrix, float* dL_dview,
+    const float* gt_depth, int track_off, int map_off,
+    float* scratch, void* stream);
+
+/* ---- full variant ----------------------------------------------------------------------- */
+
+/* replaces F/cuda_rasterizer/rasterizer.h:31-59.  out_uncertainty is the accumulated
+ * alpha*T ("opacity_map").  *num_related receives the number of valid (pixel, Gaussian)
+ * pairs (the second int of the reference's tuple). */
+GSR_API int gsr_full_forward(
+    gsr_alloc_fn geom_alloc, void* geom_ctx,
+    gsr_alloc_fn binning_alloc, void* binning_ctx,
+    gsr_alloc_fn img_alloc, void* img_ctx,
+    int P, int D, int M,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    float* out_color, float* out_depth, float* out_uncertainty, int* radii,
+    const float* gt_depth, void* stream, int* num_rendered, int* num_related);
+
+/* replaces F/cuda_rasterizer/rasterizer.h:61-102.  Same gradient outputs as the light
+ * variant; dL_dview[16].  The reference's per-pair scratch lists (dpixel_dgc, gau_id_list,
+ * pix_id_list, dpixel_dndcs, dpixel_dinvcovs, ddepth_dndcs, ddepth_dinvcovs) and per-Gaussian
+ * Jacobian tables do not exist here: the pose gradient is reduced per Gaussian on chip. */
+GSR_API int gsr_full_backward(
+    int P, int D, int M, int R,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, const int* radii,
+    char* geom_buffer, char* binning_buffer, char* img_buffer,
+    const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dpix_uncertainty,
+    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+    float* dL_dscale, float* dL_drot,
+    const float* perspec_matrix, float* dL_dview,
+    const float* gt_depth, float* scratch, void* stream);
+
+/* replaces Rasterizer::markVisible (rasterizer.h:24-29): present[i] = view-space z > 0.2.
+ * `present` is one byte per Gaussian (0/1). */
+GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, unsigned char* present, void* stream);
+
+/* Debug / test aid: decode the private geometry buffer into caller arrays (any may be NULL):
+ * depths[P], means2D[P,2], conic_opacity[P,4], rgb[P,3], cov3D[P,6], tiles_touched[P],
+ * clamped[P,3] (bytes). */
+GSR_API int gsr_decode_geometry(const char* geom_buffer, int P, float* depths, float* means2D,
+                        float* conic_opacity, float* rgb, float* cov3D,
+                        uint32_t* tiles_touched, unsigned char* clamped, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H */
