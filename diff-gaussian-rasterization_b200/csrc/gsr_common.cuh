@@ -123,10 +123,32 @@ size_t sort_temp_bytes(size_t N, int end_bit);
 // ---- device math ---------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// ---- pinned arithmetic -----------------------------------------------------------------------
+// The blend has hard thresholds (alpha < 15/255, T < 1e-4, T crossing 0.5, radius ceil, tile rect
+// casts) and -light's backward restores T from 1 - sum(alpha*T), so a 1-ulp difference in conic /
+// alpha against the reference is amplified to ~1e-3 in gradients.  To be bit-identical to the
+// reference's sm_100 build the per-Gaussian state and the per-pair power / alpha are written with
+// explicit round-to-nearest intrinsics (no compiler-chosen FMA contraction) in exactly the
+// association nvcc 12.9 gives the reference sources (read off its SASS; DESIGN.md "bit parity").
+#define GSR_MUL(a, b) __fmul_rn((a), (b))
+#define GSR_ADD(a, b) __fadd_rn((a), (b))
+#define GSR_SUB(a, b) __fsub_rn((a), (b))
+#define GSR_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define GSR_DIV(a, b) __fdiv_rn((a), (b))
+#define GSR_RCP(a) __frcp_rn((a))
+#define GSR_SQRT(a) __fsqrt_rn((a))
+
+// a0*b0 + a1*b1 + a2*b2 the way the reference build evaluates every 3-term product sum:
+// the MIDDLE product is rounded, the first and the last are fused.
+__device__ __forceinline__ float dot3_mid(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return GSR_FMA(a2, b2, GSR_FMA(a0, b0, GSR_MUL(a1, b1)));
+}
+
 struct M3 {  // column-major: c[col][row], same convention as glm::mat3
   float c[3][3];
 };
 
+// generic column-major product, compiler-contracted (backward only: tolerance 1e-3)
 __device__ __forceinline__ M3 m3_mul(const M3& A, const M3& B) {
   M3 R;
 #pragma unroll
@@ -146,17 +168,30 @@ __device__ __forceinline__ M3 m3_transpose(const M3& A) {
   return R;
 }
 
+// row k of  M * (p,1)  for a column-major 4x4:  m[k]*x + m[4+k]*y + m[8+k]*z + m[12+k]
+__device__ __forceinline__ float xform_row(const float* m, int k, const float3& p) {
+  return GSR_ADD(dot3_mid(m[k], p.x, m[4 + k], p.y, m[8 + k], p.z), m[12 + k]);
+}
+
 __device__ __forceinline__ float3 xform_point_4x3(const float3& p, const float* m) {
-  return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
-                     m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
-                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+  return make_float3(xform_row(m, 0, p), xform_row(m, 1, p), xform_row(m, 2, p));
 }
 
 __device__ __forceinline__ float4 xform_point_4x4(const float3& p, const float* m) {
-  return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
-                     m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
-                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
-                     m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+  return make_float4(xform_row(m, 0, p), xform_row(m, 1, p), xform_row(m, 2, p), xform_row(m, 3, p));
+}
+
+// Per-pair Gaussian exponent  -0.5*(A dx^2 + C dy^2) - B dx dy  (forward.cu:351), pinned:
+// fma(fma(dx, dx*A, dy*(dy*C)), -0.5, -(dy*(dx*B))).  Shared by forward and backward so both make
+// the same skip decisions.
+__device__ __forceinline__ float pair_power(float A, float B, float C, float dx, float dy) {
+  const float q = GSR_FMA(dx, GSR_MUL(dx, A), GSR_MUL(dy, GSR_MUL(dy, C)));
+  return GSR_FMA(q, -0.5f, -GSR_MUL(dy, GSR_MUL(dx, B)));
+}
+
+// alpha = min(0.99, opacity * exp(power))
+__device__ __forceinline__ float pair_alpha(float opacity, float G) {
+  return fminf(kAlphaMax, GSR_MUL(opacity, G));
 }
 
 // ndc -> pixel; the reference evaluates this in double (auxiliary.h:41-44) and rounds once.

@@ -22,96 +22,137 @@ __device__ __forceinline__ float3 ld3(const float* p, int idx) {
 }
 
 // 3D covariance from scale + (un-normalised, as in the reference forward.cu:127) quaternion.
+// Sigma = M^T M with M = S R; every M entry is the single product s_row * R[col][row]; the
+// rotation entries and the 3-term sums follow the reference build's association (SASS-derived).
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 s, float mod, const float4 q,
                                                      float* cov3D) {
-  M3 S;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) S.c[i][j] = (i == j) ? 1.0f : 0.0f;
-  S.c[0][0] = mod * s.x;
-  S.c[1][1] = mod * s.y;
-  S.c[2][2] = mod * s.z;
   const float r = q.x, x = q.y, y = q.z, z = q.w;
-  M3 R;
-  R.c[0][0] = 1.f - 2.f * (y * y + z * z); R.c[0][1] = 2.f * (x * y - r * z); R.c[0][2] = 2.f * (x * z + r * y);
-  R.c[1][0] = 2.f * (x * y + r * z); R.c[1][1] = 1.f - 2.f * (x * x + z * z); R.c[1][2] = 2.f * (y * z - r * x);
-  R.c[2][0] = 2.f * (x * z - r * y); R.c[2][1] = 2.f * (y * z + r * x); R.c[2][2] = 1.f - 2.f * (x * x + y * y);
-  const M3 Mm = m3_mul(S, R);
-  const M3 Sigma = m3_mul(m3_transpose(Mm), Mm);
-  cov3D[0] = Sigma.c[0][0];
-  cov3D[1] = Sigma.c[0][1];
-  cov3D[2] = Sigma.c[0][2];
-  cov3D[3] = Sigma.c[1][1];
-  cov3D[4] = Sigma.c[1][2];
-  cov3D[5] = Sigma.c[2][2];
+  const float xz = GSR_MUL(x, z), rx = GSR_MUL(r, x), rz = GSR_MUL(r, z);
+  const float yy = GSR_MUL(y, y), zz = GSR_MUL(z, z);
+  const float xz_p_ry = GSR_FMA(r, y, xz);    // x*z + r*y
+  const float xz_m_ry = GSR_FMA(-r, y, xz);   // x*z - r*y
+  const float yz_m_rx = GSR_FMA(y, z, -rx);   // y*z - r*x
+  const float yz_p_rx = GSR_FMA(y, z, rx);    // y*z + r*x
+  const float xy_m_rz = GSR_FMA(x, y, -rz);   // x*y - r*z
+  const float xy_p_rz = GSR_FMA(x, y, rz);    // x*y + r*z
+  const float xx_p_yy = GSR_FMA(x, x, yy);
+  const float yy_p_zz = GSR_ADD(yy, zz);
+  const float xx_p_zz = GSR_FMA(x, x, zz);
+  // R as glm stores it: Rg[col][row]
+  float Rg[3][3];
+  Rg[0][0] = GSR_SUB(1.f, GSR_ADD(yy_p_zz, yy_p_zz)); Rg[0][1] = GSR_ADD(xy_m_rz, xy_m_rz); Rg[0][2] = GSR_ADD(xz_p_ry, xz_p_ry);
+  Rg[1][0] = GSR_ADD(xy_p_rz, xy_p_rz); Rg[1][1] = GSR_SUB(1.f, GSR_ADD(xx_p_zz, xx_p_zz)); Rg[1][2] = GSR_ADD(yz_m_rx, yz_m_rx);
+  Rg[2][0] = GSR_ADD(xz_m_ry, xz_m_ry); Rg[2][1] = GSR_ADD(yz_p_rx, yz_p_rx); Rg[2][2] = GSR_SUB(1.f, GSR_ADD(xx_p_yy, xx_p_yy));
+  const float sc[3] = {GSR_MUL(mod, s.x), GSR_MUL(mod, s.y), GSR_MUL(mod, s.z)};
+  float Mm[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) Mm[c][rr] = GSR_MUL(sc[rr], Rg[c][rr]);
+  // Sigma[c][r] = sum_k M[r][k] * M[c][k]
+#define SIG(c, rr) dot3_mid(Mm[rr][0], Mm[c][0], Mm[rr][1], Mm[c][1], Mm[rr][2], Mm[c][2])
+  cov3D[0] = SIG(0, 0);
+  cov3D[1] = SIG(0, 1);
+  cov3D[2] = SIG(0, 2);
+  cov3D[3] = SIG(1, 1);
+  cov3D[4] = SIG(1, 2);
+  cov3D[5] = SIG(2, 2);
+#undef SIG
 }
 
 // EWA projection of the 3D covariance (Zwicker et al. 2002, eqs. 29/31) with the reference's
-// 1.3*tanfov clamp and 0.3 px^2 low-pass (forward.cu:74-113).
+// 1.3*tanfov clamp and 0.3 px^2 low-pass (forward.cu:74-113).  cov = T^T V^T T with T = W J;
+// J's third column and second/first off-diagonal entries are zero, so T[0][r] = W0r*J00 + W2r*J02
+// and T[1][r] = W1r*J11 + W2r*J12 (first product rounded, second fused).
 __device__ __forceinline__ float3 cov2d_ewa(const float3& mean, float fx, float fy, float tanx,
                                             float tany, const float* cov3D, const float* view) {
   float3 t = xform_point_4x3(mean, view);
-  const float limx = 1.3f * tanx;
-  const float limy = 1.3f * tany;
-  const float txtz = t.x / t.z;
-  const float tytz = t.y / t.z;
-  t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-  t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
-  M3 J;
-  J.c[0][0] = fx / t.z; J.c[0][1] = 0.0f;     J.c[0][2] = -(fx * t.x) / (t.z * t.z);
-  J.c[1][0] = 0.0f;     J.c[1][1] = fy / t.z; J.c[1][2] = -(fy * t.y) / (t.z * t.z);
-  J.c[2][0] = 0.0f;     J.c[2][1] = 0.0f;     J.c[2][2] = 0.0f;
-  M3 Wm;
-  Wm.c[0][0] = view[0]; Wm.c[0][1] = view[4]; Wm.c[0][2] = view[8];
-  Wm.c[1][0] = view[1]; Wm.c[1][1] = view[5]; Wm.c[1][2] = view[9];
-  Wm.c[2][0] = view[2]; Wm.c[2][1] = view[6]; Wm.c[2][2] = view[10];
-  const M3 T = m3_mul(Wm, J);
-  M3 V;
-  V.c[0][0] = cov3D[0]; V.c[0][1] = cov3D[1]; V.c[0][2] = cov3D[2];
-  V.c[1][0] = cov3D[1]; V.c[1][1] = cov3D[3]; V.c[1][2] = cov3D[4];
-  V.c[2][0] = cov3D[2]; V.c[2][1] = cov3D[4]; V.c[2][2] = cov3D[5];
-  M3 cov = m3_mul(m3_mul(m3_transpose(T), m3_transpose(V)), T);
-  cov.c[0][0] += 0.3f;
-  cov.c[1][1] += 0.3f;
-  return make_float3(cov.c[0][0], cov.c[0][1], cov.c[1][1]);
+  const float limx = GSR_MUL(1.3f, tanx);
+  const float limy = GSR_MUL(1.3f, tany);
+  const float txtz = GSR_DIV(t.x, t.z);
+  const float tytz = GSR_DIV(t.y, t.z);
+  t.x = GSR_MUL(fminf(limx, fmaxf(-limx, txtz)), t.z);
+  t.y = GSR_MUL(fminf(limy, fmaxf(-limy, tytz)), t.z);
+  const float tz2 = GSR_MUL(t.z, t.z);
+  const float J00 = GSR_DIV(fx, t.z);
+  const float J02 = GSR_DIV(-GSR_MUL(fx, t.x), tz2);
+  const float J11 = GSR_DIV(fy, t.z);
+  const float J12 = GSR_DIV(-GSR_MUL(fy, t.y), tz2);
+  // W[col][row] (glm) = view rotation block: W[0]=(v0,v4,v8) W[1]=(v1,v5,v9) W[2]=(v2,v6,v10)
+  const float W0[3] = {view[0], view[4], view[8]};
+  const float W1[3] = {view[1], view[5], view[9]};
+  const float W2[3] = {view[2], view[6], view[10]};
+  float T0[3], T1[3];
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr) {
+    T0[rr] = GSR_FMA(W2[rr], J02, GSR_MUL(W0[rr], J00));
+    T1[rr] = GSR_FMA(W2[rr], J12, GSR_MUL(W1[rr], J11));
+  }
+  // symmetric V[k][c]
+  const float V[3][3] = {{cov3D[0], cov3D[1], cov3D[2]}, {cov3D[1], cov3D[3], cov3D[4]}, {cov3D[2], cov3D[4], cov3D[5]}};
+  // A = T^T V^T : A[c][r] = T[r][0]*V[0][c] + T[r][1]*V[1][c] + T[r][2]*V[2][c],  r in {0,1}
+  float A0[3], A1[3];  // A?[c] = A[c][r=?]
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    A0[c] = dot3_mid(T0[0], V[0][c], T0[1], V[1][c], T0[2], V[2][c]);
+    A1[c] = dot3_mid(T1[0], V[0][c], T1[1], V[1][c], T1[2], V[2][c]);
+  }
+  // cov[c][r] = A[0][r]*T[c][0] + A[1][r]*T[c][1] + A[2][r]*T[c][2]
+  const float c00 = dot3_mid(A0[0], T0[0], A0[1], T0[1], A0[2], T0[2]);
+  const float c01 = dot3_mid(A1[0], T0[0], A1[1], T0[1], A1[2], T0[2]);  // col 0, row 1
+  const float c11 = dot3_mid(A1[0], T1[0], A1[1], T1[1], A1[2], T1[2]);
+  return make_float3(GSR_ADD(c00, 0.3f), c01, GSR_ADD(c11, 0.3f));
 }
 
 // SH (degree <= 3) -> RGB about the view direction; +0.5, clamp at 0 and remember which
-// channels were clamped (forward.cu:20-71).
+// channels were clamped (forward.cu:20-71).  Each basis coefficient is built left to right
+// ((C*y)*(poly)) and every term is fused into the running sum, as in the reference build.
 __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 pos, const float3 campos,
                                             const float* __restrict__ sh, unsigned char& clamp_bits) {
-  float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
-  const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-  dir.x = dir.x / len;
-  dir.y = dir.y / len;
-  dir.z = dir.z / len;
-#define SHC(k, ch) sh[3 * (k) + (ch)]
+  const float dx = GSR_SUB(pos.x, campos.x), dy = GSR_SUB(pos.y, campos.y), dz = GSR_SUB(pos.z, campos.z);
+  const float len = GSR_SQRT(dot3_mid(dx, dx, dy, dy, dz, dz));
+  const float x = GSR_DIV(dx, len), y = GSR_DIV(dy, len), z = GSR_DIV(dz, len);
+  float coef[16];
+  int ncoef = 1;
+  coef[0] = kSH0;
+  if (deg > 0) {
+    ncoef = 4;
+    coef[1] = -GSR_MUL(kSH1, y);
+    coef[2] = GSR_MUL(kSH1, z);
+    coef[3] = -GSR_MUL(kSH1, x);
+    if (deg > 1) {
+      ncoef = 9;
+      const float xx = GSR_MUL(x, x), yy = GSR_MUL(y, y), zz = GSR_MUL(z, z);
+      const float xy = GSR_MUL(x, y), yz = GSR_MUL(y, z), xz = GSR_MUL(x, z);
+      const float zz2 = GSR_ADD(zz, zz);
+      coef[4] = GSR_MUL(kSH2[0], xy);
+      coef[5] = GSR_MUL(kSH2[1], yz);
+      coef[6] = GSR_MUL(kSH2[2], GSR_SUB(GSR_SUB(zz2, xx), yy));
+      coef[7] = GSR_MUL(kSH2[3], xz);
+      const float xx_m_yy = GSR_SUB(xx, yy);
+      coef[8] = GSR_MUL(kSH2[4], xx_m_yy);
+      if (deg > 2) {
+        ncoef = 16;
+        const float p4 = GSR_SUB(GSR_FMA(zz, 4.0f, -xx), yy);  // 4zz - xx - yy
+        coef[9] = GSR_MUL(GSR_MUL(kSH3[0], y), GSR_FMA(xx, 3.0f, -yy));
+        coef[10] = GSR_MUL(GSR_MUL(kSH3[1], xy), z);
+        coef[11] = GSR_MUL(GSR_MUL(kSH3[2], y), p4);
+        coef[12] = GSR_MUL(GSR_MUL(kSH3[3], z), GSR_FMA(yy, -3.0f, GSR_FMA(xx, -3.0f, zz2)));
+        coef[13] = GSR_MUL(GSR_MUL(kSH3[4], x), p4);
+        coef[14] = GSR_MUL(GSR_MUL(kSH3[5], z), xx_m_yy);
+        coef[15] = GSR_MUL(GSR_MUL(kSH3[6], x), GSR_FMA(yy, -3.0f, xx));
+      }
+    }
+  }
   float res[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    float v = kSH0 * SHC(0, ch);
-    if (deg > 0) {
-      const float x = dir.x, y = dir.y, z = dir.z;
-      v = v - kSH1 * y * SHC(1, ch) + kSH1 * z * SHC(2, ch) - kSH1 * x * SHC(3, ch);
-      if (deg > 1) {
-        const float xx = x * x, yy = y * y, zz = z * z;
-        const float xy = x * y, yz = y * z, xz = x * z;
-        v = v + kSH2[0] * xy * SHC(4, ch) + kSH2[1] * yz * SHC(5, ch) +
-            kSH2[2] * (2.0f * zz - xx - yy) * SHC(6, ch) + kSH2[3] * xz * SHC(7, ch) +
-            kSH2[4] * (xx - yy) * SHC(8, ch);
-        if (deg > 2) {
-          v = v + kSH3[0] * y * (3.0f * xx - yy) * SHC(9, ch) + kSH3[1] * xy * z * SHC(10, ch) +
-              kSH3[2] * y * (4.0f * zz - xx - yy) * SHC(11, ch) +
-              kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHC(12, ch) +
-              kSH3[4] * x * (4.0f * zz - xx - yy) * SHC(13, ch) +
-              kSH3[5] * z * (xx - yy) * SHC(14, ch) + kSH3[6] * x * (xx - 3.0f * yy) * SHC(15, ch);
-        }
-      }
-    }
-    res[ch] = v + 0.5f;
+    float v = GSR_MUL(kSH0, sh[ch]);
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+      if (k < ncoef) v = GSR_FMA(coef[k], sh[3 * k + ch], v);
+    res[ch] = GSR_ADD(v, 0.5f);
   }
-#undef SHC
   clamp_bits = (unsigned char)((res[0] < 0.f ? 1 : 0) | (res[1] < 0.f ? 2 : 0) | (res[2] < 0.f ? 4 : 0));
   return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
 }
@@ -179,8 +220,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       break;
     }
     const float4 p_hom = xform_point_4x4(p_orig, proj);
-    const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-    const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+    const float p_w = GSR_RCP(GSR_ADD(p_hom.w, 0.0000001f));
+    const float3 p_proj = make_float3(GSR_MUL(p_hom.x, p_w), GSR_MUL(p_hom.y, p_w), GSR_MUL(p_hom.z, p_w));
 
     float cov_local[6];
     const float* cov3D;
@@ -196,15 +237,16 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     }
 
     const float3 cov = cov2d_ewa(p_orig, fx, fy, tanx, tany, cov3D, view);
-    const float det = (cov.x * cov.z - cov.y * cov.y);
+    const float det = GSR_FMA(cov.x, cov.z, -GSR_MUL(cov.y, cov.y));
     if (det == 0.0f) break;
-    const float det_inv = 1.f / det;
-    const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+    const float det_inv = GSR_RCP(det);
+    const float3 conic = make_float3(GSR_MUL(cov.z, det_inv), GSR_MUL(cov.y, -det_inv), GSR_MUL(cov.x, det_inv));
 
-    const float mid = 0.5f * (cov.x + cov.z);
-    const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-    const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-    const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+    const float mid = GSR_MUL(0.5f, GSR_ADD(cov.x, cov.z));
+    const float disc = GSR_SQRT(fmaxf(0.1f, GSR_FMA(mid, mid, -det)));
+    const float lambda1 = GSR_ADD(mid, disc);
+    const float lambda2 = GSR_SUB(mid, disc);
+    const float my_radius = ceilf(GSR_MUL(3.f, GSR_SQRT(fmaxf(lambda1, lambda2))));
     const float2 pix = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
     uint2 rmin, rmax;
     tile_rect(pix.x, pix.y, (int)my_radius, grid_x, grid_y, rmin, rmax);

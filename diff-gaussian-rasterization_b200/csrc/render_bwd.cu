@@ -131,13 +131,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       const int pos = walk - (i * kTileThreads + j) - 1;  // 0-based list position
       const float4 r0 = s_r0[j];
       const float4 r1 = s_r1[j];
-      const float dx = r0.x - pixfx, dy = r0.y - pixfy;
-      const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
+      const float dx = GSR_SUB(r0.x, pixfx), dy = GSR_SUB(r0.y, pixfy);
+      const float power = pair_power(r0.z, r0.w, r1.x, dx, dy);
       bool valid = (pos < last_contributor) && !(power > 0.0f) && !(power < r1.z);
       float G = 0.f, alpha = 0.f;
       if (valid) {
         G = expf(power);
-        alpha = fminf(kAlphaMax, r1.y * G);
+        alpha = pair_alpha(r1.y, G);
         valid = !(alpha < kAlphaMin);
       }
       if (!__any_sync(0xffffffffu, valid)) continue;

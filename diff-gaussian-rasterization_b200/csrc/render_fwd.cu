@@ -81,30 +81,31 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       ++contributor;
       const float4 r0 = s_r0[j];
       const float4 r1 = s_r1[j];
-      const float dx = r0.x - pixfx, dy = r0.y - pixfy;
-      const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
+      const float dx = GSR_SUB(r0.x, pixfx), dy = GSR_SUB(r0.y, pixfy);
+      const float power = pair_power(r0.z, r0.w, r1.x, dx, dy);
       if (power > 0.0f) continue;
       if (power < r1.z) continue;  // cannot reach 15/255 (see preprocess_fwd: power_cut)
-      const float alpha = fminf(kAlphaMax, r1.y * expf(power));
+      const float alpha = pair_alpha(r1.y, expf(power));
       if (alpha < kAlphaMin) continue;
 
       if (VARIANT == kLight) {
-        const float test_T = T * (1 - alpha);
+        const float test_T = GSR_MUL(T, GSR_SUB(1.f, alpha));
         if (test_T < kTmin) {
           done = true;
           continue;
         }
         const float4 r2 = s_r2[j];
         const float depth = r1.w;
-        C0 += r2.x * alpha * T;
-        C1 += r2.y * alpha * T;
-        C2 += r2.z * alpha * T;
-        Wsum += alpha * T;
-        D += depth * alpha * T;
+        C0 = GSR_FMA(T, GSR_MUL(alpha, r2.x), C0);
+        C1 = GSR_FMA(T, GSR_MUL(alpha, r2.y), C1);
+        C2 = GSR_FMA(T, GSR_MUL(alpha, r2.z), C2);
+        Wsum = GSR_FMA(T, alpha, Wsum);
+        D = GSR_FMA(T, GSR_MUL(alpha, depth), D);
         if (T > 0.5f && test_T < 0.5f) {
           Dmed = depth;
           const int id = s_id[j];
-          atomicAdd(gau_unc + id, ((depth - gt)) * (depth - gt) * alpha * T);
+          const float dg = GSR_SUB(depth, gt);
+          atomicAdd(gau_unc + id, GSR_MUL(T, GSR_MUL(alpha, GSR_MUL(dg, dg))));
           atomicAdd(gau_px + id, 1);
         }
         T = test_T;
@@ -112,14 +113,14 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       } else {
         const float4 r2 = s_r2[j];
         const float depth = r1.w;
-        C0 += r2.x * alpha * T;
-        C1 += r2.y * alpha * T;
-        C2 += r2.z * alpha * T;
-        D += depth * alpha * T;
-        Wsum += alpha * T;
+        C0 = GSR_FMA(T, GSR_MUL(alpha, r2.x), C0);
+        C1 = GSR_FMA(T, GSR_MUL(alpha, r2.y), C1);
+        C2 = GSR_FMA(T, GSR_MUL(alpha, r2.z), C2);
+        D = GSR_FMA(T, GSR_MUL(alpha, depth), D);
+        Wsum = GSR_FMA(T, alpha, Wsum);
         if (valid == 0) first = contributor;
         ++valid;
-        T = T * (1 - alpha);
+        T = GSR_MUL(T, GSR_SUB(1.f, alpha));
         last_contributor = contributor;
         if (T < kTmin) done = true;
       }
@@ -129,9 +130,9 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   if (inside) {
     const size_t HW = (size_t)H * (size_t)W;
     n_contrib[pix_id] = last_contributor;
-    out_color[0 * HW + pix_id] = C0 + T * bg[0];
-    out_color[1 * HW + pix_id] = C1 + T * bg[1];
-    out_color[2 * HW + pix_id] = C2 + T * bg[2];
+    out_color[0 * HW + pix_id] = GSR_FMA(bg[0], T, C0);
+    out_color[1 * HW + pix_id] = GSR_FMA(bg[1], T, C1);
+    out_color[2 * HW + pix_id] = GSR_FMA(bg[2], T, C2);
     out_depth[pix_id] = D;
     out_aux0[pix_id] = Wsum;
     if (VARIANT == kLight) {

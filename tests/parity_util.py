@@ -1,0 +1,166 @@
+"""Shared helpers of the parity tests: run one variant (ours or the reference build) through the
+public Python API on seeded inputs, run the CPU oracle on the same inputs, compare.
+
+Tolerances are BASELINE.json's: forward 1e-4 absolute (colour / depth / opacity / median),
+gradients 1e-3 relative (relative to the largest magnitude of the tensor, plus a per-element
+relative test).  Hard thresholds in the blend (alpha < 15/255, T < 1e-4, T crossing 0.5) can flip
+on 1-ulp differences, so image comparisons report the COUNT of pixels outside tolerance and allow
+a small budget of flips.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+FWD_ATOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+def settings_for(mod, variant, cam, scene, device, sh_degree=3, track_off=False, map_off=False,
+                 debug=False):
+    d = lambda t: t.to(device)
+    common = dict(image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                  bg=d(scene.bg), scale_modifier=1.0, viewmatrix=d(cam.viewmatrix),
+                  projmatrix=d(cam.projmatrix), sh_degree=sh_degree, campos=d(cam.campos),
+                  prefiltered=False, perspec_matrix=d(cam.perspec_matrix))
+    if variant == "light":
+        common.update(debug=debug, track_off=track_off, map_off=map_off)
+    return mod.GaussianRasterizationSettings(**common)
+
+
+def run_variant(mod, variant, cam, scene, cot, device="cuda:0", use_sh=True, sh_degree=3,
+                track_off=False, map_off=False, backward=True, cov_precomp=None):
+    """Returns (outputs, grads) as dicts of numpy arrays."""
+    d = lambda t, rg=False: t.to(device).clone().requires_grad_(rg)
+    means3D = d(scene.means3D, True)
+    means2D = torch.zeros_like(means3D, requires_grad=True)
+    opac = d(scene.opacities, True)
+    scales = d(scene.scales, True)
+    rots = d(scene.rotations, True)
+    shs = d(scene.shs, True) if use_sh else None
+    cols = None if use_sh else d(scene.colors, True)
+    view = d(cam.viewmatrix, True)
+    gt = scene.gt_depth.to(device)
+    cov = None
+    if cov_precomp is not None:
+        cov = d(cov_precomp, True)
+        scales_in, rots_in = None, None
+    else:
+        scales_in, rots_in = scales, rots
+    rs = settings_for(mod, variant, cam, scene, device, sh_degree, track_off, map_off)
+    rast = mod.GaussianRasterizer(rs)
+    res = rast(means3D=means3D, means2D=means2D, opacities=opac, shs=shs, colors_precomp=cols,
+               scales=scales_in, rotations=rots_in, cov3D_precomp=cov, viewmatrix=view, gt_depth=gt)
+    ccol, caux = cot
+    if variant == "light":
+        color, radii, depth, dmed, dvar, omap, gunc, gpx = res
+        outs = dict(color=color, radii=radii, depth=depth, depth_median=dmed, depth_var=dvar,
+                    opacity_map=omap, gau_uncertainty=gunc, gau_related_pixels=gpx)
+        loss = ((color * ccol.to(device)).sum() + (depth * caux[0].to(device)).sum() +
+                (dmed * caux[1].to(device)).sum() + (dvar * caux[2].to(device)).sum())
+    else:
+        color, radii, depth, unc = res
+        outs = dict(color=color, radii=radii, depth=depth, uncertainty=unc)
+        loss = ((color * ccol.to(device)).sum() + (depth * caux[0].to(device)).sum() +
+                (unc * caux[1].to(device)).sum())
+    grads = {}
+    if backward:
+        loss.backward()
+        grads = dict(means3D=means3D.grad, means2D=means2D.grad, opacities=opac.grad,
+                     viewmatrix=view.grad)
+        if cov is None:
+            grads.update(scales=scales.grad, rotations=rots.grad)
+        else:
+            grads.update(cov3D=cov.grad)
+        if use_sh:
+            grads["shs"] = shs.grad
+        else:
+            grads["colors"] = cols.grad
+    np_ = lambda t: None if t is None else t.detach().cpu().numpy()
+    return {k: np_(v) for k, v in outs.items()}, {k: np_(v) for k, v in grads.items()}
+
+
+def run_oracle(variant, cam, scene, cot, use_sh=True, sh_degree=3, track_off=False, map_off=False,
+               backward=True, precision="f32"):
+    orc = ge.load_oracle()
+    return orc.run(variant, cam, scene, cot, use_sh=use_sh, sh_degree=sh_degree,
+                   track_off=track_off, map_off=map_off, backward=backward, precision=precision)
+
+
+# ---- comparisons ---------------------------------------------------------------------------
+
+def image_mismatch(a, b, atol=FWD_ATOL):
+    """(#elements outside atol, max abs diff, #elements)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    diff = np.abs(a - b)
+    return int((diff > atol).sum()), float(diff.max()) if diff.size else 0.0, int(diff.size)
+
+
+def grad_mismatch(a, b, rtol=GRAD_RTOL):
+    """Relative error statistics of a gradient tensor.
+    Returns (global_rel = max|a-b| / max|b|, frac_bad = share of elements with
+    |a-b| > rtol*(|b| + 1e-2*max|b|))."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0, 0.0
+    scale = float(np.abs(b).max())
+    if scale == 0.0:
+        return float(np.abs(a).max()), float((np.abs(a) > 0).mean())
+    diff = np.abs(a - b)
+    return float(diff.max() / scale), float((diff > rtol * (np.abs(b) + 1e-2 * scale)).mean())
+
+
+def compare_runs(outs_a, grads_a, outs_b, grads_b, flip_budget=2e-4, grad_budget=2e-3,
+                 label_a="ours", label_b="ref"):
+    """Compare two (outputs, grads) pairs; returns (ok, report lines)."""
+    ok = True
+    lines = []
+    for k in outs_a:
+        a, b = outs_a[k], outs_b.get(k)
+        if b is None:
+            continue
+        if k in ("radii", "gau_related_pixels"):
+            nbad = int((np.asarray(a) != np.asarray(b)).sum())
+            good = nbad <= max(1, int(flip_budget * a.size))
+            lines.append("%-20s int mismatches %d / %d %s" % (k, nbad, a.size, "" if good else "FAIL"))
+        elif k == "gau_uncertainty":
+            g, fb = grad_mismatch(a, b)
+            good = fb <= grad_budget
+            lines.append("%-20s rel %.3e frac_bad %.3e %s" % (k, g, fb, "" if good else "FAIL"))
+        else:
+            nbad, mx, n = image_mismatch(a, b)
+            good = nbad <= max(2, int(flip_budget * n))
+            lines.append("%-20s >%.0e: %d / %d  max %.3e %s" % (k, FWD_ATOL, nbad, n, mx, "" if good else "FAIL"))
+        ok &= good
+    for k in grads_a:
+        a, b = grads_a[k], grads_b.get(k)
+        if a is None or b is None:
+            continue
+        g, fb = grad_mismatch(a, b)
+        good = (g <= 5 * GRAD_RTOL and fb <= grad_budget) if k != "viewmatrix" else g <= GRAD_RTOL
+        lines.append("grad %-15s global_rel %.3e frac_bad %.3e %s" % (k, g, fb, "" if good else "FAIL"))
+        ok &= good
+    return ok, lines
+
+
+def smoke_check(variant, device="cuda:0"):
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(96, 64)
+    scene = sc.make_scene(600, cam, (2.0, 10.0), seed=3)
+    cot = sc.make_cotangents(cam, 3 if variant == "light" else 2)
+    mod = ge.load_variant(variant)
+    outs, grads = run_variant(mod, variant, cam, scene, cot, device=device)
+    o_outs, o_grads = run_oracle(variant, cam, scene, cot)
+    ok, lines = compare_runs(outs, grads, o_outs, o_grads, flip_budget=2e-3, grad_budget=2e-2,
+                             label_b="oracle")
+    if not ok:
+        raise AssertionError("smoke parity vs oracle failed:\n" + "\n".join(lines))
+    return "parity vs CPU oracle ok (%d checks)" % len(lines)
