@@ -5,6 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "gsr_common.cuh"
 
@@ -12,8 +15,67 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/1, /*tight_tiles=*/0};
+Options g_opts = {/*exact_ng=*/1, /*tight_tiles=*/0, /*stage_timing=*/0};
+
+// Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
+struct StageTimer {
+  struct Rec { int stage; int launches; cudaEvent_t a, b; };
+  std::mutex mu;
+  std::vector<Rec> pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_pairs;
+  double ms[ST_COUNT] = {0};
+  long long scopes[ST_COUNT] = {0};
+  long long launches[ST_COUNT] = {0};
+
+  int begin(int stage, int nlaunch, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (pending.size() >= 16384) drain_locked();
+    Rec r{stage, nlaunch, nullptr, nullptr};
+    if (!free_pairs.empty()) {
+      r.a = free_pairs.back().first; r.b = free_pairs.back().second;
+      free_pairs.pop_back();
+    } else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    cudaEventRecord(r.a, s);
+    pending.push_back(r);
+    return (int)pending.size() - 1;
+  }
+  void end(int slot, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (slot >= 0 && slot < (int)pending.size()) cudaEventRecord(pending[slot].b, s);
+  }
+  void drain_locked() {
+    for (Rec& r : pending) {
+      float t = 0.f;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+        ms[r.stage] += t;
+        scopes[r.stage] += 1;
+        launches[r.stage] += r.launches;
+      } else {
+        cudaGetLastError();
+      }
+      free_pairs.emplace_back(r.a, r.b);
+    }
+    pending.clear();
+  }
+};
+StageTimer& stage_timer() {
+  static StageTimer* t = new StageTimer();  // leaked on purpose: events outlive static destruction
+  return *t;
+}
+const char* const kStageNames[ST_COUNT] = {"preprocess_fwd", "scan", "emit_keys", "radix_sort",
+                                           "tile_ranges", "render_fwd", "render_bwd",
+                                           "preprocess_bwd", "memset", "other"};
 }  // namespace
+
+StageScope::StageScope(int stage, cudaStream_t s, int nlaunch) : slot(-1), stream(s) {
+  if (g_opts.stage_timing) slot = stage_timer().begin(stage, nlaunch, s);
+}
+StageScope::~StageScope() {
+  if (slot >= 0) stage_timer().end(slot, stream);
+}
 
 Options& options() { return g_opts; }
 
@@ -96,7 +158,10 @@ int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinS
   if (!img_chunk) { set_error("image allocator returned NULL for %zu bytes", img_need); return GSR_E_ALLOC; }
   ImgState::carve(img, img_chunk, HW, tiles, variant);
 
-  GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
+  {
+    StageScope st(ST_MEMSET, a.stream);
+    GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
+  }
   int rc = launch_preprocess_fwd(a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations,
                                  a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, cam,
                                  a.radii, g, a.prefiltered != 0, a.debug != 0, a.stream);
@@ -138,6 +203,7 @@ static int* option_slot(const char* key) {
   if (!key) return nullptr;
   if (!strcmp(key, "exact_ng")) return &g_opts.exact_ng;
   if (!strcmp(key, "tight_tiles")) return &g_opts.tight_tiles;
+  if (!strcmp(key, "stage_timing")) return &g_opts.stage_timing;
   return nullptr;
 }
 
@@ -153,6 +219,23 @@ int gsr_get_option(const char* key) {
   int* s = option_slot(key);
   if (!s) { set_error("unknown option '%s'", key ? key : "(null)"); return GSR_E_INVALID; }
   return *s;
+}
+
+int gsr_stage_times(double* ms, long long* scopes, long long* launches, int reset) {
+  StageTimer& t = stage_timer();
+  std::lock_guard<std::mutex> lk(t.mu);
+  t.drain_locked();
+  for (int i = 0; i < ST_COUNT; ++i) {
+    if (ms) ms[i] = t.ms[i];
+    if (scopes) scopes[i] = t.scopes[i];
+    if (launches) launches[i] = t.launches[i];
+    if (reset) { t.ms[i] = 0; t.scopes[i] = 0; t.launches[i] = 0; }
+  }
+  return GSR_OK;
+}
+
+const char* gsr_stage_name(int stage) {
+  return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : "";
 }
 
 int gsr_light_forward(
@@ -193,8 +276,11 @@ int gsr_light_forward(
   Camera cam; GeomState g; BinState b; ImgState img;
   rc = forward_front(a, kLight, cam, g, b, img, num_rendered);
   if (rc != GSR_OK) return rc;
-  GSR_CUDA_OK(cudaMemsetAsync(gau_uncertainty, 0, (size_t)P * sizeof(float), s));
-  GSR_CUDA_OK(cudaMemsetAsync(gau_related_pixels, 0, (size_t)P * sizeof(int), s));
+  {
+    StageScope st(ST_MEMSET, s, 2);
+    GSR_CUDA_OK(cudaMemsetAsync(gau_uncertainty, 0, (size_t)P * sizeof(float), s));
+    GSR_CUDA_OK(cudaMemsetAsync(gau_related_pixels, 0, (size_t)P * sizeof(int), s));
+  }
   return launch_render_fwd_light(cam, g, b, img, background, gt_depth, out_color, out_depth,
                                  out_median_depth, out_alpha, out_depth_var, gau_uncertainty,
                                  gau_related_pixels, debug != 0, s);
@@ -281,7 +367,10 @@ int gsr_light_backward(
   if (rc != GSR_OK) return rc;
   float* acc = scratch;
   float* partials = scratch + (size_t)P * kAccStride;
-  GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
+  {
+    StageScope st(ST_MEMSET, s);
+    GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
+  }
   const bool want_gauss = !map_off, want_pose = !track_off;
   if (want_gauss || want_pose) {
     BlendGrads cot{dL_dpix, dL_dpix_depth, dL_dpix_median_depth, dL_dpix_depth_var};
@@ -326,7 +415,10 @@ int gsr_full_backward(
   if (rc != GSR_OK) return rc;
   float* acc = scratch;
   float* partials = scratch + (size_t)P * kAccStride;
-  GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
+  {
+    StageScope st(ST_MEMSET, s);
+    GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
+  }
   BlendGrads cot{dL_dpix, dL_dpix_depth, nullptr, dL_dpix_uncertainty};
   rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, false, s);
   if (rc != GSR_OK) return rc;

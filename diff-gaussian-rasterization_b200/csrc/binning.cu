@@ -126,9 +126,12 @@ int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_al
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
                 cudaStream_t stream) {
   const int tiles = cam.grid_x * cam.grid_y;
-  GSR_CUDA_OK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_bytes, g.tiles_touched, g.offsets,
-                                            P, stream));
-  GSR_LAUNCH_OK(debug, stream);
+  {
+    StageScope st(ST_SCAN, stream);
+    GSR_CUDA_OK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_bytes, g.tiles_touched,
+                                              g.offsets, P, stream));
+    GSR_LAUNCH_OK(debug, stream);
+  }
 
   // The one host<->device synchronisation of the forward: the duplicate count sizes the
   // binning buffer (the reference blocks in the same place).
@@ -148,21 +151,31 @@ int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_al
   }
   BinState::carve(b, chunk, N, sort_bytes);
 
-  GSR_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, stream));
+  {
+    StageScope st(ST_MEMSET, stream);
+    GSR_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, stream));
+  }
   if (N == 0) return GSR_OK;
 
-  emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.offsets, radii, cam.grid_x,
-                                                        cam.grid_y, b.keys_unsorted,
-                                                        b.vals_unsorted);
-  GSR_LAUNCH_OK(debug, stream);
-
-  GSR_CUDA_OK(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_bytes, b.keys_unsorted, b.keys,
-                                              b.vals_unsorted, b.vals, (int)N, 0, end_bit,
-                                              stream));
-  GSR_LAUNCH_OK(debug, stream);
-
-  tile_ranges_kernel<<<(N + 255) / 256, 256, 0, stream>>>((int)N, b.keys, img.ranges);
-  GSR_LAUNCH_OK(debug, stream);
+  {
+    StageScope st(ST_EMIT, stream);
+    emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.offsets, radii, cam.grid_x,
+                                                          cam.grid_y, b.keys_unsorted,
+                                                          b.vals_unsorted);
+    GSR_LAUNCH_OK(debug, stream);
+  }
+  {
+    StageScope st(ST_SORT, stream);
+    GSR_CUDA_OK(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_bytes, b.keys_unsorted, b.keys,
+                                                b.vals_unsorted, b.vals, (int)N, 0, end_bit,
+                                                stream));
+    GSR_LAUNCH_OK(debug, stream);
+  }
+  {
+    StageScope st(ST_RANGES, stream);
+    tile_ranges_kernel<<<(N + 255) / 256, 256, 0, stream>>>((int)N, b.keys, img.ranges);
+    GSR_LAUNCH_OK(debug, stream);
+  }
   return GSR_OK;
 }
 

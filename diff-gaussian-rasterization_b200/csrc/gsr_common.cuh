@@ -42,8 +42,34 @@ enum AccSlot {
 struct Options {
   int exact_ng;
   int tight_tiles;
+  int stage_timing;
 };
 Options& options();
+
+// ---- stage timing (gsr_stage_times in the C ABI) ---------------------------------------------
+enum Stage {
+  ST_PRE_FWD = 0,   // per-Gaussian forward
+  ST_SCAN,          // prefix sum of tiles_touched (+ the count read-back)
+  ST_EMIT,          // (tile | depth) key emission
+  ST_SORT,          // device radix sort
+  ST_RANGES,        // per-tile ranges
+  ST_RENDER_FWD,    // forward tile blend
+  ST_RENDER_BWD,    // backward tile blend
+  ST_PRE_BWD,       // per-Gaussian backward + pose reduction
+  ST_MEMSET,        // zero-fills issued by the library
+  ST_OTHER,
+  ST_COUNT
+};
+static_assert(ST_COUNT == GSR_STAGE_COUNT, "stage table out of sync with gsr_b200.h");
+
+// RAII scope: records a start/stop event pair on `stream` when options().stage_timing is set;
+// `launches` = number of kernels launched inside the scope.
+struct StageScope {
+  StageScope(int stage, cudaStream_t stream, int launches = 1);
+  ~StageScope();
+  int slot;
+  cudaStream_t stream;
+};
 
 // ---- error plumbing ------------------------------------------------------------------------
 void set_error(const char* fmt, ...);

@@ -483,6 +483,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   const int blocks = (P + kBwdThreads - 1) / kBwdThreads;
   const size_t smem = (shs != nullptr && want_gauss) ? sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1) : 0;
   const float* cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
+  StageScope st(ST_PRE_BWD, stream, 2);
   if (!want_gauss) {
     // light + map_off: every per-Gaussian gradient is zero (light backward.cu:593,609,654,666;
     // rasterizer_impl.cu:467)

@@ -305,6 +305,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
   const size_t smem = (shs != nullptr && colors_precomp == nullptr)
                           ? sizeof(float) * kPreThreads * (size_t)(M * 3 + 1) : 0;
   const int blocks = (P + kPreThreads - 1) / kPreThreads;
+  StageScope st(ST_PRE_FWD, stream);
   preprocess_fwd_kernel<<<blocks, kPreThreads, smem, stream>>>(
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,

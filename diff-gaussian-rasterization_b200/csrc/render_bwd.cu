@@ -224,6 +224,7 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
                       const float* alphas, const BlendGrads& cot, float* acc, bool debug,
                       cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
+  StageScope st(ST_RENDER_BWD, stream);
   if (variant == kLight) {
     render_bwd_kernel<kLight><<<grid, kTileThreads, 0, stream>>>(
         img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas,

@@ -174,6 +174,7 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
                             float* out_var, float* gau_unc, int* gau_px, bool debug,
                             cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
+  StageScope st(ST_RENDER_FWD, stream);
   render_fwd_kernel<kLight><<<grid, kTileThreads, 0, stream>>>(
       img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, out_color, out_depth,
       out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
@@ -186,6 +187,7 @@ int launch_render_fwd_full(const Camera& cam, const GeomState& g, const BinState
                            ImgState& img, const float* bg, float* out_color, float* out_depth,
                            float* out_unc, bool count_related, bool debug, cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
+  StageScope st(ST_RENDER_FWD, stream);
   render_fwd_kernel<kFull><<<grid, kTileThreads, 0, stream>>>(
       img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, nullptr, out_color, out_depth,
       out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,

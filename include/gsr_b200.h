@@ -70,12 +70,24 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
 /* Tuning switches (process-wide, not part of the reference surface).
  *   "exact_ng"      1 (default): gsr_full_forward returns the exact number of valid
  *                   (pixel, Gaussian) pairs like the reference; 0: skip the count + sync, return 0.
+ *   "stage_timing"  1: record per-stage CUDA events (see gsr_stage_times); 0 (default): off.
  *   "tight_tiles"   1: drop (tile, Gaussian) duplicates that provably cannot reach the
  *                   alpha >= 15/255 threshold inside the tile (outputs unchanged, num_rendered
  *                   smaller than the reference's); 0 (default): the reference's rectangle rule.
  * Returns the previous value, or GSR_E_INVALID for an unknown key. */
 GSR_API int gsr_set_option(const char* key, int value);
 GSR_API int gsr_get_option(const char* key);
+
+/* Stage timing (bench / profiling aid, not part of the reference surface).
+ * With gsr_set_option("stage_timing", 1) every entry point brackets each pipeline stage with
+ * CUDA events recorded on the caller's stream.  gsr_stage_times() waits for the recorded events
+ * and returns, per stage, the accumulated device milliseconds, the number of timed scopes and the
+ * number of kernels this library launched inside them (CUB's internal kernels are counted as one
+ * launch per call); `reset` != 0 clears the accumulators afterwards.  Arrays hold
+ * GSR_STAGE_COUNT entries; any may be NULL. */
+#define GSR_STAGE_COUNT 10
+GSR_API int gsr_stage_times(double* ms, long long* scopes, long long* launches, int reset);
+GSR_API const char* gsr_stage_name(int stage);
 
 /* ---- light variant ---------------------------------------------------------------------- */
 

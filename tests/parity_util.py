@@ -87,10 +87,11 @@ def run_variant(mod, variant, cam, scene, cot, device="cuda:0", use_sh=True, sh_
 
 
 def run_oracle(variant, cam, scene, cot, use_sh=True, sh_degree=3, track_off=False, map_off=False,
-               backward=True, precision="f32"):
+               backward=True, precision="f32", cov_precomp=None):
     orc = ge.load_oracle()
     return orc.run(variant, cam, scene, cot, use_sh=use_sh, sh_degree=sh_degree,
-                   track_off=track_off, map_off=map_off, backward=backward, precision=precision)
+                   track_off=track_off, map_off=map_off, backward=backward, precision=precision,
+                   cov_precomp=cov_precomp)
 
 
 # ---- comparisons ---------------------------------------------------------------------------
@@ -164,3 +165,44 @@ def smoke_check(variant, device="cuda:0"):
     if not ok:
         raise AssertionError("smoke parity vs oracle failed:\n" + "\n".join(lines))
     return "parity vs CPU oracle ok (%d checks)" % len(lines)
+
+
+# ---- golden vectors (outputs of the reference CUDA build, tests/golden/make_golden.py) ---------
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_cases():
+    if not os.path.isdir(GOLDEN_DIR):
+        return []
+    return sorted(f[len("case_"):-len(".npz")] for f in os.listdir(GOLDEN_DIR)
+                  if f.startswith("case_") and f.endswith(".npz"))
+
+
+def load_golden(name):
+    """-> dict(variant, cam, scene, cot, use_sh, sh_degree, cov, modes, data)."""
+    sc = ge.load_scene_module()
+    z = np.load(os.path.join(GOLDEN_DIR, "case_%s.npz" % name))
+    W, H, deg, use_sh, has_cov = [int(v) for v in z["meta"]]
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(z[k]))
+    cam = sc.Camera(W, H, float(z["tanfov"][0]), float(z["tanfov"][1]), t("in_viewmatrix"),
+                    t("in_projmatrix"), t("in_perspec"), t("in_campos"), t("in_w2c"))
+    scene = sc.Scene(t("in_means3D"), t("in_scales"), t("in_rotations"), t("in_opacities"),
+                     t("in_shs"), t("in_colors"), t("in_bg"), t("in_gt_depth"))
+    aux = t("in_cot_aux")
+    cot = (t("in_cot_color"), [aux[i] for i in range(aux.shape[0])])
+    modes = sorted({(k[1] == "1", k[2] == "1") for k in z.files if k.startswith("m") and k[3] == "_"})
+    return dict(variant="light" if name.startswith("light") else "full", cam=cam, scene=scene,
+                cot=cot, use_sh=bool(use_sh), sh_degree=deg, cov=t("in_cov3D") if has_cov else None,
+                modes=modes, data=z)
+
+
+def golden_expected(data, track_off=False, map_off=False):
+    tag = "m%d%d_" % (int(track_off), int(map_off))
+    outs = {k[len(tag) + 4:]: data[k] for k in data.files if k.startswith(tag + "out_")}
+    grads = {k[len(tag) + 5:]: data[k] for k in data.files if k.startswith(tag + "grad_")}
+    return outs, grads
+
+
+def golden_geometry(data):
+    return {k[5:]: data[k] for k in data.files if k.startswith("geom_")}

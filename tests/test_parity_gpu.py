@@ -1,0 +1,392 @@
+"""GPU parity tests (run on the B200 box: python -m pytest tests -m gpu).
+
+The CUDA path (libgsr_b200.so through the torch shim, and directly through the C ABI with ctypes)
+is compared with
+  * the CPU oracle on the same seeded inputs (sizes the oracle finishes in seconds),
+  * the committed golden vectors = outputs of the reference's CUDA build (tests/golden/),
+  * the reference build itself when baseline/_ref travelled to the box,
+and, at BASELINE.json's full size (1 M Gaussians, 1920x1080), through size-independent properties.
+Tolerances are the north star's: forward 1e-4 abs, gradients 1e-3 rel (parity_util.FWD_ATOL /
+GRAD_RTOL); integer outputs (radii, tiles, counts) must match exactly.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import parity_util as pu
+
+ge = pu.ge
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _scene(P, W, H, sig=(2.0, 10.0), seed=3, backdrop=False):
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(W, H)
+    return sc, cam, sc.make_scene(P, cam, sig, seed=seed, backdrop=backdrop)
+
+
+def _n_aux(variant):
+    return 3 if variant == "light" else 2
+
+
+# ---- CUDA vs CPU oracle ------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant,track_off,map_off", [
+    ("light", False, False), ("light", True, False), ("light", False, True), ("full", False, False)])
+def test_cuda_matches_oracle(built, variant, track_off, map_off):
+    sc, cam, scene = _scene(1500, 160, 96, seed=21, backdrop=(variant == "full"))
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    outs, grads = pu.run_variant(mod, variant, cam, scene, cot, track_off=track_off, map_off=map_off)
+    o_outs, o_grads = pu.run_oracle(variant, cam, scene, cot, track_off=track_off, map_off=map_off)
+    ok, lines = pu.compare_runs(outs, grads, o_outs, o_grads, flip_budget=1e-3, grad_budget=1e-2,
+                                label_b="oracle")
+    assert ok, "\n".join(lines)
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+@pytest.mark.parametrize("use_sh,deg", [(True, 0), (True, 1), (True, 2), (False, 0)])
+def test_cuda_matches_oracle_colour_paths(built, variant, use_sh, deg):
+    sc, cam, scene = _scene(800, 100, 70, seed=22, backdrop=(variant == "full"))  # ragged size
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    outs, grads = pu.run_variant(mod, variant, cam, scene, cot, use_sh=use_sh, sh_degree=deg)
+    o_outs, o_grads = pu.run_oracle(variant, cam, scene, cot, use_sh=use_sh, sh_degree=deg)
+    if variant == "full":
+        # -full's pose pass is only defined for fully covered, in-image tiles;
+        # a 100x70 image has ragged tiles, so dL_dview is compared in the aligned tests instead
+        grads.pop("viewmatrix"), o_grads.pop("viewmatrix")
+    ok, lines = pu.compare_runs(outs, grads, o_outs, o_grads, flip_budget=1e-3, grad_budget=1e-2)
+    assert ok, "\n".join(lines)
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_cuda_matches_oracle_precomputed_covariance(built, variant):
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(pu.GOLDEN_DIR, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    sc, cam, scene = _scene(700, 96, 64, seed=23, backdrop=(variant == "full"))
+    cov = mg.cov3d_of(scene)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    outs, grads = pu.run_variant(mod, variant, cam, scene, cot, cov_precomp=cov)
+    o_outs, o_grads = pu.run_oracle(variant, cam, scene, cot, cov_precomp=cov)
+    ok, lines = pu.compare_runs(outs, grads, o_outs, o_grads, flip_budget=1e-3, grad_budget=1e-2)
+    assert ok, "\n".join(lines)
+
+
+# ---- CUDA vs golden vectors of the reference build ---------------------------------------------
+
+CASES = pu.golden_cases()
+
+
+@pytest.mark.skipif(not CASES, reason="no golden vectors committed yet")
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_reference_golden(built, name):
+    g = pu.load_golden(name)
+    mod = built.load_variant(g["variant"])
+    for (track_off, map_off) in g["modes"]:
+        exp_o, exp_g = pu.golden_expected(g["data"], track_off, map_off)
+        outs, grads = pu.run_variant(mod, g["variant"], g["cam"], g["scene"], g["cot"],
+                                     use_sh=g["use_sh"], sh_degree=g["sh_degree"], track_off=track_off,
+                                     map_off=map_off, cov_precomp=g["cov"])
+        assert (outs["radii"] == exp_o["radii"]).all()
+        ok, lines = pu.compare_runs(outs, grads, exp_o, exp_g, flip_budget=0.0, grad_budget=1e-3,
+                                    label_b="reference")
+        assert ok, "%s track_off=%s map_off=%s\n%s" % (name, track_off, map_off, "\n".join(lines))
+        # forward images are bit-identical to the reference build (pinned arithmetic)
+        for k in ("color", "depth"):
+            assert np.array_equal(outs[k], exp_o[k]), "%s not bit-identical in %s" % (k, name)
+
+
+@pytest.mark.skipif(not CASES, reason="no golden vectors committed yet")
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_geometry_bit_identical_to_reference_golden(built, name):
+    g = pu.load_golden(name)
+    geo, radii, nr = _decode_ours(built, g["variant"], g["cam"], g["scene"], g["use_sh"], g["sh_degree"], g["cov"])
+    ref = pu.golden_geometry(g["data"])
+    exp_o, _ = pu.golden_expected(g["data"], *g["modes"][0])
+    vis = exp_o["radii"] > 0
+    assert nr == int(g["data"]["num_rendered"][0])
+    assert (radii == exp_o["radii"]).all()
+    for k in ("depth", "means2D", "conic_opacity", "rgb"):
+        a = np.ascontiguousarray(geo[k][vis]).view(np.uint32)
+        b = np.ascontiguousarray(ref[k][vis]).view(np.uint32)
+        assert np.array_equal(a, b), "%s differs bitwise from the reference build" % k
+    if g["cov"] is None:
+        assert np.array_equal(np.ascontiguousarray(geo["cov3D"][vis]).view(np.uint32),
+                              np.ascontiguousarray(ref["cov3D"][vis]).view(np.uint32))
+    assert (geo["tiles_touched"][vis] == ref["tiles_touched"][vis]).all()
+    assert (geo["clamped"][vis].astype(bool) == ref["clamped"][vis].astype(bool)).all()
+
+
+def _decode_ours(built, variant, cam, scene, use_sh=True, deg=3, cov=None):
+    mod = built.load_variant(variant)
+    E = torch.Tensor([])
+    d = lambda t: t.to(DEV)
+    args = [d(scene.bg), d(scene.means3D), E if use_sh else d(scene.colors), d(scene.opacities),
+            E if cov is not None else d(scene.scales), E if cov is not None else d(scene.rotations), 1.0,
+            d(cov) if cov is not None else E, d(cam.viewmatrix), d(scene.gt_depth), d(cam.projmatrix),
+            cam.tanfovx, cam.tanfovy, cam.H, cam.W, d(scene.shs) if use_sh else E, deg, d(cam.campos), False]
+    if variant == "light":
+        r = mod._C.rasterize_gaussians(*args, False)
+        radii, geom = r[6], r[7]
+    else:
+        r = mod._C.rasterize_gaussians(*args)
+        radii, geom = r[5], r[6]
+    P = scene.means3D.shape[0]
+    lib = ctypes.CDLL(built.core_library_path())
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=DEV)
+    o = dict(depth=f(P), means2D=f(P, 2), conic_opacity=f(P, 4), rgb=f(P, 3), cov3D=f(P, 6),
+             tiles_touched=torch.empty(P, dtype=torch.int32, device=DEV),
+             clamped=torch.empty(P, 3, dtype=torch.uint8, device=DEV))
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.gsr_decode_geometry(vp(geom), P, vp(o["depth"]), vp(o["means2D"]), vp(o["conic_opacity"]),
+                                 vp(o["rgb"]), vp(o["cov3D"]), vp(o["tiles_touched"]), vp(o["clamped"]),
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in o.items()}
+    out["tiles_touched"] = out["tiles_touched"].view(np.uint32)
+    return out, radii.cpu().numpy(), int(r[0])
+
+
+# ---- CUDA vs the reference build, live (when baseline/_ref is on the box) ----------------------
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_cuda_matches_reference_build_live(built, variant):
+    ref = ge.load_reference(variant)
+    if ref is None:
+        pytest.skip("baseline/_ref not present on this box")
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(320, 240)
+    scene = sc.make_scene(10_000, cam, (2.0, 12.0), seed=0, backdrop=(variant == "full"))  # config C1
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    o_m, g_m = pu.run_variant(mod, variant, cam, scene, cot)
+    o_r, g_r = pu.run_variant(ref, variant, cam, scene, cot)
+    ok, lines = pu.compare_runs(o_m, g_m, o_r, g_r, flip_budget=0.0, grad_budget=1e-3)
+    assert ok, "\n".join(lines)
+    assert np.array_equal(o_m["color"], o_r["color"])
+
+
+# ---- straight through the C ABI (no torch shim) ------------------------------------------------
+
+ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+def test_c_abi_light_forward_backward_matches_oracle(built):
+    sc, cam, scene = _scene(900, 96, 64, seed=31)
+    cot = sc.make_cotangents(cam, 3)
+    lib = ctypes.CDLL(built.core_library_path())
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    lib.gsr_backward_scratch_floats.restype = ctypes.c_size_t
+    P, M, W, H = scene.means3D.shape[0], 16, cam.W, cam.H
+    d = lambda t: t.to(DEV).contiguous()
+    t_in = dict(bg=d(scene.bg), means=d(scene.means3D), shs=d(scene.shs), op=d(scene.opacities),
+                sc=d(scene.scales), rot=d(scene.rotations), view=d(cam.viewmatrix),
+                proj=d(cam.projmatrix), campos=d(cam.campos), gt=d(scene.gt_depth),
+                persp=d(cam.perspec_matrix))
+    bufs = {}
+
+    def make_alloc(tag):
+        def cb(_ctx, nbytes):
+            bufs[tag] = torch.empty(max(int(nbytes), 1) + 256, dtype=torch.uint8, device=DEV)
+            return (bufs[tag].data_ptr() + 255) // 256 * 256
+        return ALLOC_FN(cb)
+    a_geom, a_bin, a_img = make_alloc("geom"), make_alloc("bin"), make_alloc("img")
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=DEV)
+    color, depth, median, alpha, var = f(3, H, W), f(H, W), f(H, W), f(H, W), f(H, W)
+    gunc, gpx, radii = f(P), torch.empty(P, dtype=torch.int32, device=DEV), torch.empty(P, dtype=torch.int32, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    nr = ctypes.c_int(0)
+    cf = ctypes.c_float
+    rc = lib.gsr_light_forward(
+        a_geom, None, a_bin, None, a_img, None, P, 3, M, p(t_in["bg"]), W, H, p(t_in["means"]),
+        p(t_in["shs"]), None, p(t_in["op"]), p(t_in["sc"]), cf(1.0), p(t_in["rot"]), None,
+        p(t_in["view"]), p(t_in["proj"]), p(t_in["campos"]), cf(cam.tanfovx), cf(cam.tanfovy), 0,
+        p(color), p(depth), p(median), p(alpha), p(t_in["gt"]), p(var), p(gunc), p(gpx), p(radii), 0,
+        None, ctypes.byref(nr))
+    assert rc == 0, lib.gsr_last_error()
+    torch.cuda.synchronize()
+    o_outs, o_grads = pu.run_oracle("light", cam, scene, cot)
+    assert nr.value == o_outs["_num_rendered"]
+    assert (radii.cpu().numpy() == o_outs["radii"]).all()
+    assert pu.image_mismatch(color.cpu().numpy(), o_outs["color"])[0] <= 4
+    assert pu.image_mismatch(median.cpu().numpy()[None], o_outs["depth_median"])[0] <= 4
+
+    gc, gd, gm, gv = d(cot[0]), d(cot[1][0]), d(cot[1][1]), d(cot[1][2])
+    g = dict(m2=f(P, 3), conic=f(P, 4), opac=f(P), col=f(P, 3), dep=f(P), m3=f(P, 3), cov=f(P, 6),
+             sh=f(P, M, 3), scl=f(P, 3), rot=f(P, 4), view=f(16))
+    scratch = f(lib.gsr_backward_scratch_floats(P))
+    geom_p = (bufs["geom"].data_ptr() + 255) // 256 * 256
+    bin_p = (bufs["bin"].data_ptr() + 255) // 256 * 256
+    img_p = (bufs["img"].data_ptr() + 255) // 256 * 256
+    rc = lib.gsr_light_backward(
+        P, 3, M, nr.value, p(t_in["bg"]), W, H, p(t_in["means"]), p(t_in["shs"]), None, p(alpha),
+        p(t_in["sc"]), cf(1.0), p(t_in["rot"]), None, p(t_in["view"]), p(t_in["proj"]),
+        p(t_in["campos"]), cf(cam.tanfovx), cf(cam.tanfovy), p(radii), ctypes.c_void_p(geom_p),
+        ctypes.c_void_p(bin_p), ctypes.c_void_p(img_p), p(gc), p(gd), p(gm), p(gv), p(g["m2"]),
+        p(g["conic"]), p(g["opac"]), p(g["col"]), p(g["dep"]), p(g["m3"]), p(g["cov"]), p(g["sh"]),
+        p(g["scl"]), p(g["rot"]), 0, p(t_in["persp"]), p(g["view"]), p(t_in["gt"]), 0, 0, p(scratch), None)
+    assert rc == 0, lib.gsr_last_error()
+    torch.cuda.synchronize()
+    for ours, key in ((g["m3"], "means3D"), (g["sh"], "shs"), (g["scl"], "scales"), (g["rot"], "rotations")):
+        rel, bad = pu.grad_mismatch(ours.cpu().numpy().reshape(o_grads[key].shape), o_grads[key])
+        assert rel < 5e-3 and bad < 1e-2, key
+    rel, _ = pu.grad_mismatch(g["view"].cpu().numpy().reshape(4, 4), o_grads["viewmatrix"])
+    assert rel < 1e-3
+
+
+def test_c_abi_reports_errors(built):
+    lib = ctypes.CDLL(built.core_library_path())
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    null_alloc = ALLOC_FN(lambda ctx, n: None)
+    x = torch.zeros(64, device=DEV)
+    p = ctypes.c_void_p(x.data_ptr())
+    nr = ctypes.c_int(0)
+    cf = ctypes.c_float
+    # neither SH nor precomputed colours
+    rc = lib.gsr_light_forward(null_alloc, None, null_alloc, None, null_alloc, None, 4, 0, 0, p, 16, 16,
+                               p, None, None, p, p, cf(1.0), p, None, p, p, p, cf(1.0), cf(1.0), 0,
+                               p, p, p, p, p, p, p, p, p, 0, None, ctypes.byref(nr))
+    assert rc == -1 and b"SH" in lib.gsr_last_error()
+    # allocator failure
+    rc = lib.gsr_light_forward(null_alloc, None, null_alloc, None, null_alloc, None, 4, 0, 0, p, 16, 16,
+                               p, None, p, p, p, cf(1.0), p, None, p, p, p, cf(1.0), cf(1.0), 0,
+                               p, p, p, p, p, p, p, p, p, 0, None, ctypes.byref(nr))
+    assert rc == -3 and b"allocator" in lib.gsr_last_error()
+
+
+# ---- edge cases ----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_empty_scene_and_all_culled(built, variant):
+    sc, cam, scene = _scene(64, 48, 32, seed=5)
+    mod = built.load_variant(variant)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    empty = scene._replace(means3D=scene.means3D[:0], scales=scene.scales[:0], rotations=scene.rotations[:0],
+                           opacities=scene.opacities[:0], shs=scene.shs[:0], colors=scene.colors[:0])
+    outs, _ = pu.run_variant(mod, variant, cam, empty, cot, backward=False)
+    assert np.abs(outs["color"]).max() == 0  # reference returns zero-filled outputs for P == 0
+    behind = scene._replace(means3D=torch.tensor([[0.0, 0.0, -5.0]]).repeat(64, 1))
+    outs, grads = pu.run_variant(mod, variant, cam, behind, cot)
+    assert (outs["radii"] == 0).all()
+    assert np.allclose(outs["color"], scene.bg.numpy()[:, None, None])
+    assert all(np.abs(v).max() == 0 for v in grads.values() if v is not None)
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_mark_visible(built, variant):
+    sc, cam, scene = _scene(5000, 64, 48, seed=6)
+    mod = built.load_variant(variant)
+    rs = pu.settings_for(mod, variant, cam, scene, DEV)
+    vis = mod.GaussianRasterizer(rs).markVisible(scene.means3D.to(DEV)).cpu().numpy()
+    z = (scene.means3D.double() @ cam.w2c[:3, :3].double().T + cam.w2c[:3, 3].double())[:, 2].numpy()
+    sure = np.abs(z - 0.2) > 1e-5
+    assert vis.dtype == np.bool_ and (vis[sure] == (z[sure] > 0.2)).all()
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_forward_is_deterministic_and_stream_safe(built, variant):
+    sc, cam, scene = _scene(4000, 160, 96, seed=8)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    a, ga = pu.run_variant(mod, variant, cam, scene, cot)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        b, gb = pu.run_variant(mod, variant, cam, scene, cot)
+    s.synchronize()
+    for k in a:
+        if k != "gau_uncertainty":  # float atomics: order-dependent in the reference too
+            assert np.array_equal(a[k], b[k]), k
+    assert np.allclose(ga["viewmatrix"], gb["viewmatrix"], rtol=1e-4, atol=1e-3)
+
+
+def test_huge_and_tiny_splats(built):
+    """A splat covering the whole image and sub-pixel splats in the same scene."""
+    sc, cam, scene = _scene(300, 96, 64, seed=9)
+    scales = scene.scales.clone()
+    scales[0] = 50.0
+    scales[1:20] = 1e-5
+    scene = scene._replace(scales=scales)
+    cot = sc.make_cotangents(cam, 3)
+    mod = built.load_variant("light")
+    outs, grads = pu.run_variant(mod, "light", cam, scene, cot)
+    o_outs, o_grads = pu.run_oracle("light", cam, scene, cot)
+    ok, lines = pu.compare_runs(outs, grads, o_outs, o_grads, flip_budget=2e-3, grad_budget=2e-2)
+    assert ok, "\n".join(lines)
+
+
+# ---- full-size properties (config 3: 1 M Gaussians, 1920x1080) ---------------------------------
+
+@pytest.fixture(scope="module")
+def c3():
+    sc = ge.load_scene_module()
+    cam, scene = sc.config("C3")
+    return sc, cam, scene
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_full_size_properties(built, c3, variant):
+    sc, cam, scene = c3
+    mod = built.load_variant(variant)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    outs, grads = pu.run_variant(mod, variant, cam, scene, cot)
+    # (1) background compositing identity: colour(bg) - colour(0) == (1 - sum alpha*T) * bg
+    black = scene._replace(bg=torch.zeros(3))
+    outs0, _ = pu.run_variant(mod, variant, cam, black, cot, backward=False)
+    acc = outs["opacity_map" if variant == "light" else "uncertainty"]
+    lhs = outs["color"] - outs0["color"]
+    rhs = (1.0 - acc) * scene.bg.numpy()[:, None, None]
+    if variant == "light":
+        # light stops BEFORE the terminating Gaussian: T_final >= 1 - sum(alpha*T) exactly equal
+        assert np.abs(lhs - rhs).max() < 2e-5
+    else:
+        assert np.abs(lhs - rhs).max() < 2e-5
+    # (2) the other outputs do not depend on the background
+    assert np.array_equal(outs["depth"], outs0["depth"]) and np.array_equal(outs["radii"], outs0["radii"])
+    # (3) backward is linear in the cotangents
+    cot2 = (cot[0] * 2.0, [c * 2.0 for c in cot[1]])
+    _, grads2 = pu.run_variant(mod, variant, cam, scene, cot2)
+    for k in ("means3D", "opacities", "shs", "viewmatrix"):
+        rel, _ = pu.grad_mismatch(grads2[k], 2.0 * grads[k])
+        assert rel < 1e-3, k
+    # (4) culled Gaussians get exactly zero gradient
+    culled = outs["radii"] == 0
+    assert culled.any() and np.abs(grads["means3D"][culled]).max() == 0 and np.abs(grads["shs"][culled]).max() == 0
+    # (5) dL/dmeans2D has an all-zero third column (F/__init__.py:139)
+    assert np.abs(grads["means2D"][:, 2]).max() == 0
+
+
+def test_full_size_light_pose_gradient_is_outer_product_sum(built, c3):
+    """With only a colour cotangent, -light's dL/dview equals
+    sum_g (w p0 gx, w p5 gy, -w^2 (hom.x gx + hom.y gy)) (x) (m_g, 1)  with g = dL/dmean2D_g
+     — evaluated here in float64 from the returned dL/dmeans2D."""
+    sc, cam, scene = c3
+    mod = built.load_variant("light")
+    ccol, caux = sc.make_cotangents(cam, 3)
+    cot = (ccol, [torch.zeros_like(c) for c in caux])
+    _, grads = pu.run_variant(mod, "light", cam, scene, cot)
+    m = scene.means3D.double().numpy()
+    proj = cam.projmatrix.double().numpy().reshape(-1)  # flat column-major as the kernels read it
+    hom = np.stack([proj[k] * m[:, 0] + proj[4 + k] * m[:, 1] + proj[8 + k] * m[:, 2] + proj[12 + k]
+                    for k in range(4)], 1)
+    w = 1.0 / (hom[:, 3] + 1e-7)
+    p0, p5 = float(cam.perspec_matrix[0, 0]), float(cam.perspec_matrix[1, 1])
+    g = grads["means2D"].astype(np.float64)
+    a = w * p0 * g[:, 0]
+    b = w * p5 * g[:, 1]
+    c = -w * w * (hom[:, 0] * g[:, 0] + hom[:, 1] * g[:, 1])
+    m1 = np.concatenate([m, np.ones((m.shape[0], 1))], 1)
+    expect = np.zeros((4, 4))
+    for col in range(4):
+        expect[col, 0] = (a * m1[:, col]).sum()
+        expect[col, 1] = (b * m1[:, col]).sum()
+        expect[col, 2] = (c * m1[:, col]).sum()
+    rel, _ = pu.grad_mismatch(grads["viewmatrix"], expect)
+    assert rel < 1e-3, (grads["viewmatrix"], expect)
