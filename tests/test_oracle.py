@@ -60,8 +60,11 @@ def test_oracle_geometry_matches_reference_golden(name):
     vis = exp_o["radii"] > 0
     assert (r.radii == exp_o["radii"]).all()
     assert (mine["tiles_touched"][vis] == ref["tiles_touched"][vis]).all()
-    assert (mine["clamped"][vis].astype(bool) == ref["clamped"][vis].astype(bool)).all()
+    if g["use_sh"]:  # with precomputed colours the reference never writes `clamped` (uninitialised)
+        assert (mine["clamped"][vis].astype(bool) == ref["clamped"][vis].astype(bool)).all()
     for k, tol in (("depth", 1e-5), ("means2D", 1e-3), ("conic_opacity", 1e-4), ("rgb", 1e-5)):
+        if k == "rgb" and not g["use_sh"]:
+            continue  # precomputed colours are read in place: the reference leaves geom.rgb uninitialised
         a, b = np.asarray(mine[k])[vis], np.asarray(ref[k])[vis]
         scale = np.maximum(np.abs(b), 1.0)
         assert np.max(np.abs(a - b) / scale) < tol, k

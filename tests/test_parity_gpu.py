@@ -114,6 +114,8 @@ def test_cuda_geometry_bit_identical_to_reference_golden(built, name):
     assert nr == int(g["data"]["num_rendered"][0])
     assert (radii == exp_o["radii"]).all()
     for k in ("depth", "means2D", "conic_opacity", "rgb"):
+        if k == "rgb" and not g["use_sh"]:
+            continue  # precomputed colours are read in place: the reference leaves geom.rgb uninitialised
         a = np.ascontiguousarray(geo[k][vis]).view(np.uint32)
         b = np.ascontiguousarray(ref[k][vis]).view(np.uint32)
         assert np.array_equal(a, b), "%s differs bitwise from the reference build" % k
@@ -121,7 +123,8 @@ def test_cuda_geometry_bit_identical_to_reference_golden(built, name):
         assert np.array_equal(np.ascontiguousarray(geo["cov3D"][vis]).view(np.uint32),
                               np.ascontiguousarray(ref["cov3D"][vis]).view(np.uint32))
     assert (geo["tiles_touched"][vis] == ref["tiles_touched"][vis]).all()
-    assert (geo["clamped"][vis].astype(bool) == ref["clamped"][vis].astype(bool)).all()
+    if g["use_sh"]:  # with precomputed colours the reference never writes `clamped` (uninitialised)
+        assert (geo["clamped"][vis].astype(bool) == ref["clamped"][vis].astype(bool)).all()
 
 
 def _decode_ours(built, variant, cam, scene, use_sh=True, deg=3, cov=None):
