@@ -15,7 +15,7 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/1, /*tight_tiles=*/0, /*stage_timing=*/0};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {

@@ -36,6 +36,7 @@ size_t GeomState::carve(GeomState& s, char* base, int P, size_t scan_bytes) {
   s.cov3D = c.take<float>(6 * (size_t)P);
   s.clamped = c.take<unsigned char>((size_t)P);
   s.tiles_touched = c.take<uint32_t>((size_t)P);
+  s.rect = c.take<uint2>((size_t)P);
   s.offsets = c.take<uint32_t>((size_t)P);
   s.counters = c.take<uint32_t>(8);
   s.scan_temp = c.take<char>(scan_bytes);
@@ -81,18 +82,17 @@ int bits_for(uint32_t n) {
 
 __global__ void emit_keys_kernel(int P, const float4* __restrict__ rec,
                                  const uint32_t* __restrict__ offsets,
-                                 const int* __restrict__ radii, int grid_x, int grid_y,
+                                 const uint32_t* __restrict__ tiles_touched,
+                                 const uint2* __restrict__ rects, int grid_x,
                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
-  const int radius = radii[idx];
-  if (radius <= 0) return;
+  if (tiles_touched[idx] == 0) return;
   uint32_t off = (idx == 0) ? 0u : offsets[idx - 1];
-  const float4 r0 = rec[3 * (size_t)idx + 0];
-  const float4 r1 = rec[3 * (size_t)idx + 1];
-  uint2 rmin, rmax;
-  tile_rect(r0.x, r0.y, radius, grid_x, grid_y, rmin, rmax);
-  const uint64_t depth_bits = (uint64_t)__float_as_uint(r1.w);
+  const uint2 rc = rects[idx];  // the rectangle preprocess_fwd counted
+  const uint2 rmin = make_uint2(rc.x & 0xFFFFu, rc.y & 0xFFFFu);
+  const uint2 rmax = make_uint2(rc.x >> 16, rc.y >> 16);
+  const uint64_t depth_bits = (uint64_t)__float_as_uint(rec[3 * (size_t)idx + 1].w);
   for (uint32_t y = rmin.y; y < rmax.y; ++y) {
     for (uint32_t x = rmin.x; x < rmax.x; ++x) {
       const uint64_t key = ((uint64_t)(y * (uint32_t)grid_x + x) << 32) | depth_bits;
@@ -122,7 +122,7 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
 
 }  // namespace
 
-int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_alloc_fn alloc,
+int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gsr_alloc_fn alloc,
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
                 cudaStream_t stream) {
   const int tiles = cam.grid_x * cam.grid_y;
@@ -159,8 +159,8 @@ int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_al
 
   {
     StageScope st(ST_EMIT, stream);
-    emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.offsets, radii, cam.grid_x,
-                                                          cam.grid_y, b.keys_unsorted,
+    emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.offsets, g.tiles_touched,
+                                                          g.rect, cam.grid_x, b.keys_unsorted,
                                                           b.vals_unsorted);
     GSR_LAUNCH_OK(debug, stream);
   }

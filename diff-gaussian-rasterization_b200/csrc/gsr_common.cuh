@@ -117,6 +117,7 @@ struct GeomState {
   float* cov3D;            // [6P] (only when computed from scale/rotation)
   unsigned char* clamped;  // [P] bit k set <=> colour channel k clamped at 0
   uint32_t* tiles_touched; // [P]
+  uint2* rect;             // [P] tile rectangle: x = xmin | xmax << 16, y = ymin | ymax << 16
   uint32_t* offsets;       // [P] inclusive scan of tiles_touched
   uint32_t* counters;      // [8]  0: num_rendered, 1: num_related
   char* scan_temp;
@@ -233,6 +234,54 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
   rmin.y = (unsigned)min(gy, max(0, (int)((py - r) / (float)kTileY)));
   rmax.x = (unsigned)min(gx, max(0, (int)((px + r + (float)(kTileX - 1)) / (float)kTileX)));
   rmax.y = (unsigned)min(gy, max(0, (int)((py + r + (float)(kTileY - 1)) / (float)kTileY)));
+}
+
+// ---- conservative culling of pairs that cannot reach alpha >= 15/255 ---------------------------
+// A pair is blended only if power >= power_cut (= log((15/255)/opacity) - 1e-3, see preprocess_fwd),
+// i.e. if the pixel lies in the ellipse  A dx^2 + 2 B dx dy + C dy^2 <= -2 power_cut  of the stored
+// (rounded) conic.  Its axis-aligned half extents are sqrt(-2 pc C / det), sqrt(-2 pc A / det) with
+// det = A C - B^2, evaluated with Kahan's compensated 2x2 determinant so that cancellation in
+// needle-shaped splats cannot shrink the box; a relative 1e-4 and absolute 0.02 px pad cover the
+// rounding of the per-pair evaluation.  Returns 0: no pixel can pass, 1: box valid, 2: unbounded.
+__device__ __forceinline__ int cut_extent(float A, float B, float C, float pc, float& hx, float& hy) {
+  if (pc > 0.0f) return 0;
+  if (!(pc <= 0.0f)) return 2;  // NaN opacity: keep the reference's behaviour, cull nothing
+  const float w = __fmul_rn(B, B);
+  const float e = __fmaf_rn(-B, B, w);
+  const float f = __fmaf_rn(A, C, -w);
+  const float det = __fadd_rn(f, e);
+  if (!(det > 0.0f)) return 2;
+  const float k = __fdiv_rn(-2.0f * pc, det);
+  hx = __fsqrt_ru(__fmul_ru(k, C));
+  hy = __fsqrt_ru(__fmul_ru(k, A));
+  if (!(hx < 1e30f) || !(hy < 1e30f)) return 2;
+  hx = __fmaf_ru(hx, 1.0001f, 0.02f);
+  hy = __fmaf_ru(hy, 1.0001f, 0.02f);
+  return 1;
+}
+
+// 8-bit mask of the 8x4-pixel warp blocks of a 16x16 tile (bit w = block column w & 1, block row
+// w >> 1, the pixel-to-warp mapping of the blend kernels) that a splat's cut ellipse may touch.
+__device__ __forceinline__ unsigned block_mask8(const float4& r0, const float4& r1, float tx0,
+                                                float ty0) {
+  float hx, hy;
+  const int kind = cut_extent(r0.z, r0.w, r1.x, r1.z, hx, hy);
+  if (kind == 0) return 0u;
+  if (kind == 2) return 0xFFu;
+  const float x0 = r0.x - hx, x1 = r0.x + hx, y0 = r0.y - hy, y1 = r0.y + hy;
+  const unsigned col = ((x1 >= tx0 && x0 <= tx0 + 7.0f) ? 1u : 0u) |
+                       ((x1 >= tx0 + 8.0f && x0 <= tx0 + 15.0f) ? 2u : 0u);
+  unsigned mask = 0u;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float by = ty0 + 4.0f * (float)r;
+    if (y1 >= by && y0 <= by + 3.0f) mask |= col << (2 * r);
+  }
+  return mask;
+}
+
+__device__ __forceinline__ uint2 pack_rect(uint2 rmin, uint2 rmax) {
+  return make_uint2(rmin.x | (rmax.x << 16), rmin.y | (rmax.y << 16));
 }
 
 // Spherical-harmonics constants (real SH basis up to degree 3, standard values).

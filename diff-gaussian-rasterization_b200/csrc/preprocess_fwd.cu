@@ -173,7 +173,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int H, float tanx, float tany, float fx, float fy, int grid_x, int grid_y,
                       int* __restrict__ radii, float4* __restrict__ rec, float* __restrict__ cov3Ds,
                       unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                      bool prefiltered, bool tight_tiles) {
+                      uint2* __restrict__ rects, bool prefiltered, bool tight_tiles) {
   extern __shared__ float sh_smem[];  // [kPreThreads][M*3+1] when shs != nullptr
   const int base = blockIdx.x * kPreThreads;
   const int idx = base + threadIdx.x;
@@ -207,6 +207,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 
   int my_radius_i = 0;
   uint32_t my_tiles = 0;
+  uint2 my_rect = make_uint2(0u, 0u);
   unsigned char cbits = 0;
 
   const float3 p_orig = ld3(means3D, idx);
@@ -266,15 +267,34 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     const float power_cut = (opacity > 0.0f) ? (logf(kAlphaMin / opacity) - 1e-3f) : 1.0f;
 
     my_radius_i = (int)my_radius;
+    if (tight_tiles) {
+      // shrink the reference's 3-sigma rectangle to the tiles the alpha >= 15/255 ellipse can reach:
+      // tile t holds pixel centres [16t, 16t+15]
+      float hx, hy;
+      const int kind = cut_extent(conic.x, conic.y, conic.z, power_cut, hx, hy);
+      if (kind == 0) {
+        rmax = rmin;
+      } else if (kind == 1) {
+        const int tx0 = (int)ceilf((pix.x - hx - (float)(kTileX - 1)) / (float)kTileX);
+        const int tx1 = (int)floorf((pix.x + hx) / (float)kTileX) + 1;
+        const int ty0 = (int)ceilf((pix.y - hy - (float)(kTileY - 1)) / (float)kTileY);
+        const int ty1 = (int)floorf((pix.y + hy) / (float)kTileY) + 1;
+        rmin.x = (unsigned)max((int)rmin.x, min(tx0, (int)rmax.x));
+        rmin.y = (unsigned)max((int)rmin.y, min(ty0, (int)rmax.y));
+        rmax.x = (unsigned)min((int)rmax.x, max(tx1, (int)rmin.x));
+        rmax.y = (unsigned)min((int)rmax.y, max(ty1, (int)rmin.y));
+      }
+    }
     my_tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
+    my_rect = pack_rect(rmin, rmax);
     rec[3 * (size_t)idx + 0] = make_float4(pix.x, pix.y, conic.x, conic.y);
     rec[3 * (size_t)idx + 1] = make_float4(conic.z, opacity, power_cut, p_view.z);
     rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
-    (void)tight_tiles;
   } while (false);
 
   radii[idx] = my_radius_i;
   tiles_touched[idx] = my_tiles;
+  rects[idx] = my_rect;
   clamped[idx] = cbits;
 }
 
@@ -310,7 +330,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,
       cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,
-      g.tiles_touched, prefiltered, options().tight_tiles != 0);
+      g.tiles_touched, g.rect, prefiltered, options().tight_tiles != 0);
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
 }

@@ -74,6 +74,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ float4 s_r1[kTileThreads];
   __shared__ float4 s_r2[kTileThreads];
   __shared__ int s_id[kTileThreads];
+  __shared__ unsigned char s_mask[kTileThreads];
+  __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -112,22 +114,38 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
   bool mid_once = true;
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
 
   for (int i = 0; i < rounds; ++i) {
     __syncthreads();
     const int progress = i * kTileThreads + tid;
+    unsigned my_mask = 0u;
     if (progress < walk) {
       const int id = (int)point_list[range.x + (walk - progress - 1)];
       s_id[tid] = id;
       const float4* r = rec + 3 * (size_t)id;
-      s_r0[tid] = __ldg(r + 0);
-      s_r1[tid] = __ldg(r + 1);
+      const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1);
+      s_r0[tid] = q0;
+      s_r1[tid] = q1;
       s_r2[tid] = __ldg(r + 2);
+      my_mask = block_mask8(q0, q1, tile_x0, tile_y0);
     }
+    s_mask[tid] = (unsigned char)my_mask;
     __syncthreads();
 
+    // per-warp compaction: only entries whose cut ellipse can touch this warp's 8x4 block
     const int nb = min(kTileThreads, walk - i * kTileThreads);
-    for (int j = 0; j < nb; ++j) {
+    int cnt = 0;
+    for (int c = 0; c * 32 < nb; ++c) {
+      const int jj = c * 32 + lane;
+      const bool hit = (jj < nb) && ((s_mask[jj] >> warp) & 1u);
+      const unsigned ball = __ballot_sync(0xffffffffu, hit);
+      if (hit) s_list[warp][cnt + __popc(ball & ((1u << lane) - 1u))] = (unsigned char)jj;
+      cnt += __popc(ball);
+    }
+    __syncwarp();
+    for (int k = 0; k < cnt; ++k) {
+      const int j = s_list[warp][k];
       const int pos = walk - (i * kTileThreads + j) - 1;  // 0-based list position
       const float4 r0 = s_r0[j];
       const float4 r1 = s_r1[j];

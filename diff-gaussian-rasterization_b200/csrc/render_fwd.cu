@@ -40,6 +40,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ float4 s_r1[kTileThreads];
   __shared__ float4 s_r2[kTileThreads];
   __shared__ int s_id[kTileThreads];
+  __shared__ unsigned char s_mask[kTileThreads];                    // warp-block mask per entry
+  __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];  // per-warp compacted entries
   __shared__ uint32_t s_red[kTileThreads / 32];
 
   const int tid = threadIdx.x;
@@ -58,7 +60,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
   bool done = !inside;
   float T = 1.0f;
-  uint32_t contributor = 0, last_contributor = 0, first = 0, valid = 0;
+  uint32_t last_contributor = 0, first = 0, valid = 0;
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, Wsum = 0.f, Dmed = 0.f;
   float gt = 0.f;
   if (VARIANT == kLight && inside) gt = gt_depth[pix_id];
@@ -66,19 +69,36 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   for (int i = 0; i < rounds; ++i, todo -= kTileThreads) {
     if (__syncthreads_count(done) == kTileThreads) break;
     const int progress = i * kTileThreads + tid;
+    unsigned my_mask = 0u;
     if (progress < total) {
       const int id = (int)point_list[range.x + progress];
       s_id[tid] = id;
       const float4* r = rec + 3 * (size_t)id;
-      s_r0[tid] = __ldg(r + 0);
-      s_r1[tid] = __ldg(r + 1);
+      const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1);
+      s_r0[tid] = q0;
+      s_r1[tid] = q1;
       s_r2[tid] = __ldg(r + 2);
+      my_mask = block_mask8(q0, q1, tile_x0, tile_y0);
     }
+    s_mask[tid] = (unsigned char)my_mask;
     __syncthreads();
 
+    // each warp keeps only the entries whose cut ellipse can touch its 8x4 pixel block
     const int nb = min(kTileThreads, todo);
-    for (int j = 0; !done && j < nb; ++j) {
-      ++contributor;
+    int cnt = 0;
+    if (__any_sync(0xffffffffu, !done)) {
+      for (int c = 0; c * 32 < nb; ++c) {
+        const int j = c * 32 + lane;
+        const bool hit = (j < nb) && ((s_mask[j] >> warp) & 1u);
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[warp][cnt + __popc(ball & ((1u << lane) - 1u))] = (unsigned char)j;
+        cnt += __popc(ball);
+      }
+      __syncwarp();
+    }
+    for (int k = 0; !done && k < cnt; ++k) {
+      const int j = s_list[warp][k];
+      const uint32_t contributor = (uint32_t)(i * kTileThreads + j + 1);  // 1-based list position
       const float4 r0 = s_r0[j];
       const float4 r1 = s_r1[j];
       const float dx = GSR_SUB(r0.x, pixfx), dy = GSR_SUB(r0.y, pixfy);

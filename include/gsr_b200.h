@@ -68,12 +68,15 @@ GSR_API const char* gsr_last_error(void);
 GSR_API size_t gsr_backward_scratch_floats(int P);
 
 /* Tuning switches (process-wide, not part of the reference surface).
- *   "exact_ng"      1 (default): gsr_full_forward returns the exact number of valid
- *                   (pixel, Gaussian) pairs like the reference; 0: skip the count + sync, return 0.
+ *   "exact_ng"      1: gsr_full_forward returns the exact number of valid (pixel, Gaussian) pairs
+ *                   like the reference (costs a second host sync per forward); 0 (default): skip
+ *                   the count and the sync and return 0 — the reference's Python only hands the
+ *                   value back to the backward to size scratch lists that do not exist here.
  *   "stage_timing"  1: record per-stage CUDA events (see gsr_stage_times); 0 (default): off.
- *   "tight_tiles"   1: drop (tile, Gaussian) duplicates that provably cannot reach the
- *                   alpha >= 15/255 threshold inside the tile (outputs unchanged, num_rendered
- *                   smaller than the reference's); 0 (default): the reference's rectangle rule.
+ *   "tight_tiles"   1 (default): drop (tile, Gaussian) duplicates that provably cannot reach the
+ *                   alpha >= 15/255 threshold inside the tile (every output is unchanged bit for
+ *                   bit; num_rendered is smaller than the reference's); 0: the reference's
+ *                   3-sigma rectangle rule, num_rendered identical to the reference.
  * Returns the previous value, or GSR_E_INVALID for an unknown key. */
 GSR_API int gsr_set_option(const char* key, int value);
 GSR_API int gsr_get_option(const char* key);

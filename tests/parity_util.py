@@ -94,6 +94,25 @@ def run_oracle(variant, cam, scene, cot, use_sh=True, sh_degree=3, track_off=Fal
                    cov_precomp=cov_precomp)
 
 
+def set_option(key, value):
+    """Process-wide tuning switch of libgsr_b200.so (include/gsr_b200.h); returns the old value."""
+    import ctypes
+    lib = ctypes.CDLL(ge.core_library_path())
+    return lib.gsr_set_option(key.encode(), int(value))
+
+
+class reference_counts:
+    """Context manager: make num_rendered / num_related / tiles_touched follow the reference's
+    rules exactly (tight_tiles = 0, exact_ng = 1) so that they can be compared as integers."""
+
+    def __enter__(self):
+        self.old = (set_option("tight_tiles", 0), set_option("exact_ng", 1))
+
+    def __exit__(self, *a):
+        set_option("tight_tiles", self.old[0])
+        set_option("exact_ng", self.old[1])
+
+
 # ---- comparisons ---------------------------------------------------------------------------
 
 def image_mismatch(a, b, atol=FWD_ATOL):

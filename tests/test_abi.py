@@ -37,10 +37,10 @@ def test_scratch_size_and_options(built):
     n1, n2 = lib.gsr_backward_scratch_floats(1000), lib.gsr_backward_scratch_floats(2000)
     assert n2 > n1 >= 1000 * 16
     lib.gsr_last_error.restype = ctypes.c_char_p
+    assert lib.gsr_get_option(b"exact_ng") == 0 and lib.gsr_get_option(b"tight_tiles") == 1
+    assert lib.gsr_set_option(b"exact_ng", 1) == 0
     assert lib.gsr_get_option(b"exact_ng") == 1
-    assert lib.gsr_set_option(b"exact_ng", 0) == 1
-    assert lib.gsr_get_option(b"exact_ng") == 0
-    lib.gsr_set_option(b"exact_ng", 1)
+    lib.gsr_set_option(b"exact_ng", 0)
     assert lib.gsr_set_option(b"no_such_option", 1) == -1
     assert b"unknown option" in lib.gsr_last_error()
 
