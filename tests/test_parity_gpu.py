@@ -422,3 +422,49 @@ def test_full_size_light_pose_gradient_is_outer_product_sum(built, c3):
         expect[col, 2] = (c * m1[:, col]).sum()
     rel, _ = pu.grad_mismatch(grads["viewmatrix"], expect)
     assert rel < 1e-3, (grads["viewmatrix"], expect)
+
+
+# ---- layer-4 render() helper -------------------------------------------------------
+
+class _Gaussians:
+    def __init__(self, scene, dev):
+        self.get_xyz = scene.means3D.to(dev).requires_grad_(True)
+        self.get_opacity = scene.opacities.to(dev).requires_grad_(True)
+        self.get_scaling = scene.scales.to(dev).requires_grad_(True)
+        self.get_rotation = scene.rotations.to(dev).requires_grad_(True)
+        self.get_features = scene.shs.to(dev).requires_grad_(True)
+        self.active_sh_degree = 3
+
+
+class _Cam:
+    def __init__(self, cam, dev):
+        self.projection_matrix = cam.perspec_matrix.to(dev)
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_render_helper_matches_direct_rasterizer_call(built, variant):
+    """render() with CG-SLAM's signature returns the README's dict keys and the same tensors /
+    pose gradient as driving GaussianRasterizer by hand with scene.py's camera tensors."""
+    sc, cam, scene = _scene(2000, 160, 96, seed=51)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    rmod = ge.load_render_module()
+    g = _Gaussians(scene, DEV)
+    w2cT = cam.viewmatrix.to(DEV).requires_grad_(True)
+    kw = dict(viewmatrix=w2cT, fov=(cam.tanfovx, cam.tanfovy), HW=(cam.H, cam.W), gt_depth=scene.gt_depth.to(DEV),
+              rasterizer_module=mod)
+    if variant == "light":
+        kw.update(track_off=False, map_off=False)
+    out = rmod.render(_Cam(cam, DEV), g, None, scene.bg.to(DEV), **kw)
+    want = {"render", "depth", "opacity_map"}
+    if variant == "light":
+        want |= {"depth_median", "depth_var", "gau_uncertainty", "num_related_pixels"}
+    assert want <= set(out)
+    (out["render"] * cot[0].to(DEV)).sum().backward()
+    ref_o, ref_g = pu.run_variant(mod, variant, cam, scene, (cot[0], [torch.zeros_like(c) for c in cot[1]]))
+    assert np.abs(out["render"].detach().cpu().numpy() - ref_o["color"]).max() < 1e-5
+    assert np.abs(out["depth"].detach().cpu().numpy() - ref_o["depth"]).max() < 1e-4
+    rel, _ = pu.grad_mismatch(w2cT.grad.cpu().numpy(), ref_g["viewmatrix"])
+    assert rel < 1e-3
+    rel, _ = pu.grad_mismatch(g.get_xyz.grad.cpu().numpy(), ref_g["means3D"])
+    assert rel < 1e-3
