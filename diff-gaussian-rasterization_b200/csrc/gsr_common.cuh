@@ -27,13 +27,14 @@ enum Variant { kLight = 0, kFull = 1 };
 
 // accumulator slots (per Gaussian, written by the backward blend kernel with warp-reduced
 // atomics, consumed by the per-Gaussian backward kernel)
+// With w = G * dL/dalpha per (pixel, Gaussian) pair and (dx, dy) = mean2D - pixel:
 enum AccSlot {
-  ACC_MX = 0, ACC_MY = 1,         // dL/dmean2D
-  ACC_CA = 2, ACC_CB = 3, ACC_CC = 4,  // dL/dconic (.x .y .w of the reference's float4)
-  ACC_OP = 5,                     // dL/dopacity
+  ACC_MX = 0, ACC_MY = 1,         // S1 = sum w dx, S2 = sum w dy          -> dL/dmean2D
+  ACC_CA = 2, ACC_CB = 3, ACC_CC = 4,  // S11, S12, S22 = sum w {dx^2, dx dy, dy^2} -> dL/dconic
+  ACC_OP = 5,                     // S0 = sum w = dL/dopacity
   ACC_R = 6, ACC_G = 7, ACC_B = 8,  // dL/dcolor (sum alpha*T*dL/dpixel)
   ACC_DEPTH = 9,                  // dL/ddepth (incl. the (depth-gt)^2 term)
-  ACC_PGX = 10, ACC_PGY = 11,     // pose: dL/d(ndc) as the reference's pose pass sees it (full)
+  ACC_PGX = 10, ACC_PGY = 11,     // full: Q1, Q2 = sum q {dx, dy}, q = G * (pose weight of the pair)
   ACC_PD = 12,                    // pose: sum alpha*T*dL/dD (light: all pairs; full: front-most)
   ACC_MED = 13                    // light: sum of dL/dmedian over pixels that picked this Gaussian
 };

@@ -46,8 +46,9 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ cov3Ds, const float* __restrict__ view,
                       const float* __restrict__ proj, const float* __restrict__ campos_p,
                       const float* __restrict__ perspec, float fx, float fy, float tanx, float tany,
-                      const float* __restrict__ acc, float* __restrict__ pose_partials,
-                      GaussGradOut out, bool want_gauss, bool want_pose) {
+                      const float* __restrict__ acc, const float4* __restrict__ g_rec, int img_w,
+                      int img_h, float* __restrict__ pose_partials, GaussGradOut out,
+                      bool want_gauss, bool want_pose) {
   extern __shared__ float sh_smem[];  // [kBwdThreads][M*3+1] SH in, dL/dSH out
   __shared__ float s_pose[kBwdThreads / 32][12];
   const int base = blockIdx.x * kBwdThreads;
@@ -109,9 +110,18 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   if (live) {
     const float4* a4 = reinterpret_cast<const float4*>(acc + (size_t)idx * kAccStride);
     const float4 a0 = a4[0], a1 = a4[1], a2 = a4[2], a3 = a4[3];
-    const float g_mx = a0.x, g_my = a0.y, g_ca = a0.z, g_cb = a0.w;
-    const float g_cc = a1.x, g_op = a1.y, g_r = a1.z, g_g = a1.w;
-    const float g_b = a2.x, g_depth = a2.y, g_pgx = a2.z, g_pgy = a2.w;
+    // moments of w = G dL/dalpha (render_bwd) -> screen-space gradients with this Gaussian's conic:
+    //   dL/dmean2D.x = 0.5 W o (-A S1 - B S2),  dL/dconic = -0.5 o (S11, S12, S22),  dL/dopacity = S0
+    const float4 rec0 = g_rec[3 * (size_t)idx + 0], rec1 = g_rec[3 * (size_t)idx + 1];
+    const float cA = rec0.z, cB = rec0.w, cC = rec1.x, opac = rec1.y;
+    const float half_w_o = 0.5f * (float)img_w * opac, half_h_o = 0.5f * (float)img_h * opac;
+    const float g_mx = half_w_o * (-cA * a0.x - cB * a0.y);
+    const float g_my = half_h_o * (-cC * a0.y - cB * a0.x);
+    const float g_ca = -0.5f * opac * a0.z, g_cb = -0.5f * opac * a0.w, g_cc = -0.5f * opac * a1.x;
+    const float g_op = a1.y, g_r = a1.z, g_g = a1.w;
+    const float g_b = a2.x, g_depth = a2.y;
+    const float g_pgx = half_w_o * (-cA * a2.z - cB * a2.w);
+    const float g_pgy = half_h_o * (-cC * a2.w - cB * a2.z);
     const float g_pd = a3.x, g_med = a3.y;
 
     const float3 m = ld3(means3D, idx);
@@ -508,12 +518,12 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
       preprocess_bwd_kernel<kLight><<<blocks, kBwdThreads, smem, stream>>>(
           P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D,
           cam.view, cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx,
-          cam.tan_fovy, acc, pose_partials, out, want_gauss, want_pose);
+          cam.tan_fovy, acc, g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose);
     } else {
       preprocess_bwd_kernel<kFull><<<blocks, kBwdThreads, smem, stream>>>(
           P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D,
           cam.view, cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx,
-          cam.tan_fovy, acc, pose_partials, out, want_gauss, want_pose);
+          cam.tan_fovy, acc, g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose);
     }
     GSR_LAUNCH_OK(debug, stream);
   }

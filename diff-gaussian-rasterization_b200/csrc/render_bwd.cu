@@ -6,9 +6,12 @@
 //
 // What is different by design (B200-first, same results):
 //  * the reference issues ~10 global atomicAdd per (pixel, Gaussian) pair; here the 32 pixels of
-//    a warp (a compact 8x4 block) first reduce their 16 partial sums with a transposing
-//    butterfly (16 shuffles instead of 80) and 16 lanes then issue one coalesced 64-byte red.add
-//    into the Gaussian's accumulator record — whole warps that do not touch a Gaussian skip it;
+//    a warp (a compact 8x4 block) first reduce their 14 partial sums through a shared-memory
+//    transpose (14 stores, 4 x LDS.128 + one shuffle per reducing lane) and 14 lanes then issue
+//    one coalesced red.add into the Gaussian's 64-byte accumulator line — whole warps that do not
+//    touch a Gaussian skip it;
+//  * mean2D / conic / opacity gradients are accumulated as moments of w = G dL/dalpha over (dx, dy)
+//    and converted per Gaussian in preprocess_bwd;
 //  * the pose gradient needs no per-pixel [H*W,16] tensor (light) and no 92-byte-per-pair scratch
 //    + second tile walk (full ComputePG): every pose term is (per-pair scalar) x (per-Gaussian
 //    vector), so the per-pair scalars are summed per Gaussian here (slots ACC_PGX/PGY/PD) and
@@ -22,38 +25,14 @@ namespace gsr {
 
 namespace {
 
-// Sum v[0..15] over the 32 lanes of a warp.  On return lane L holds the total of value (L >> 1)
-// in v[0] (both lanes of a pair hold the same number).
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
-  const bool up16 = (lane & 16) != 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float send = up16 ? v[k] : v[k + 8];
-    const float keep = up16 ? v[k + 8] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  const bool up8 = (lane & 8) != 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float send = up8 ? v[k] : v[k + 4];
-    const float keep = up8 ? v[k + 4] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  const bool up4 = (lane & 4) != 0;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float send = up4 ? v[k] : v[k + 2];
-    const float keep = up4 ? v[k + 2] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const bool up2 = (lane & 2) != 0;
-  {
-    const float send = up2 ? v[0] : v[1];
-    const float keep = up2 ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  return v[0];
+constexpr int kRedVals = 14;    // accumulator slots reduced per (warp, Gaussian) hit
+constexpr int kRedStride = 36;  // floats per slot row in shared memory (144 B: 16-byte aligned rows
+                                // whose bank offsets rotate by 4, conflict-free per quarter warp)
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 template <int VARIANT>
@@ -76,6 +55,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ int s_id[kTileThreads];
   __shared__ unsigned char s_mask[kTileThreads];
   __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];
+  __shared__ __align__(16) float s_red[kTileThreads / 32][kRedVals * kRedStride];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -160,58 +140,54 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       }
       if (!__any_sync(0xffffffffu, valid)) continue;
 
-      float v[16];
+      // Per-pair partial sums.  The screen-space mean, conic and opacity gradients are all moments
+      // of w = G * dL/dalpha over (dx, dy); they are summed as moments here and turned into
+      // dL/dmean2D, dL/dconic by preprocess_bwd with the per-Gaussian conic (fewer per-pair FLOPs).
+      float v[kRedVals];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = 0.f;
+      for (int q = 0; q < kRedVals; ++q) v[q] = 0.f;
       if (valid) {
         const float4 r2 = s_r2[j];
-        const float o = r1.y;
         const float c_d = r1.w;
-        T = T / (1.f - alpha);
+        const float inv = fast_rcp(1.f - alpha);   // 1 - alpha >= 0.01
+        T = T * inv;
         const float aT = alpha * T;
+        const float one_m_la = 1.f - last_alpha;
 
-        float dL_dalpha = 0.0f;
-        ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0;
-        lc0 = r2.x;
-        dL_dalpha += (r2.x - ar0) * dLp0;
-        ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1;
-        lc1 = r2.y;
-        dL_dalpha += (r2.y - ar1) * dLp1;
-        ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2;
-        lc2 = r2.z;
-        dL_dalpha += (r2.z - ar2) * dLp2;
+        ar0 = last_alpha * lc0 + one_m_la * ar0;
+        ar1 = last_alpha * lc1 + one_m_la * ar1;
+        ar2 = last_alpha * lc2 + one_m_la * ar2;
+        lc0 = r2.x; lc1 = r2.y; lc2 = r2.z;
+        const float colour_part = (r2.x - ar0) * dLp0 + (r2.y - ar1) * dLp1 + (r2.z - ar2) * dLp2;
         v[ACC_R] = aT * dLp0;
         v[ACC_G] = aT * dLp1;
         v[ACC_B] = aT * dLp2;
-        const float colour_part = dL_dalpha;  // sum_ch (c - accum_rec) * dL/dpixel
 
-        const float c_var = (c_d - gt) * (c_d - gt);
-        adr = last_alpha * last_depth + (1.f - last_alpha) * adr;
+        const float dgt = c_d - gt;
+        const float c_var = dgt * dgt;
+        adr = last_alpha * last_depth + one_m_la * adr;
+        avr = last_alpha * last_var + one_m_la * avr;
         last_depth = c_d;
-        avr = last_alpha * last_var + (1.f - last_alpha) * avr;
         last_var = c_var;
-        dL_dalpha += (c_d - adr) * dLd;
-        dL_dalpha += (c_var - avr) * dLv;
-        v[ACC_DEPTH] = aT * dLd + dLv * aT * 2.f * (c_d - gt);
+        const float depth_part = (c_d - adr) * dLd;
+        float dL_dalpha = colour_part + depth_part + (c_var - avr) * dLv;
+        const float aTd = aT * dLd;
+        v[ACC_DEPTH] = aTd + dLv * aT * 2.f * dgt;
 
-        dL_dalpha *= T;
         last_alpha = alpha;
-        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+        dL_dalpha = dL_dalpha * T - (T_final * inv) * bg_dot_dpixel;
 
-        const float dL_dG = o * dL_dalpha;
-        const float gdx = G * dx;
-        const float gdy = G * dy;
-        const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-        const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-        v[ACC_MX] = dL_dG * dG_ddelx * ddelx_dx;
-        v[ACC_MY] = dL_dG * dG_ddely * ddely_dy;
-        v[ACC_CA] = -0.5f * gdx * dx * dL_dG;
-        v[ACC_CB] = -0.5f * gdx * dy * dL_dG;
-        v[ACC_CC] = -0.5f * gdy * dy * dL_dG;
-        v[ACC_OP] = G * dL_dalpha;
+        const float w = G * dL_dalpha;
+        const float wx = w * dx, wy = w * dy;
+        v[ACC_OP] = w;
+        v[ACC_MX] = wx;        // S1  = sum w dx
+        v[ACC_MY] = wy;        // S2  = sum w dy
+        v[ACC_CA] = wx * dx;   // S11 = sum w dx^2
+        v[ACC_CB] = wx * dy;   // S12 = sum w dx dy
+        v[ACC_CC] = wy * dy;   // S22 = sum w dy^2
 
         if (VARIANT == kLight) {
-          v[ACC_PD] = aT * dLd;
+          v[ACC_PD] = aTd;
           if (T > 0.5f && mid_once) {
             v[ACC_MED] = dLm;
             mid_once = false;
@@ -222,15 +198,31 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
           // contributor of the pixel, because dd_dv* is assigned, not accumulated (:1278-1289).
           float pa = T * colour_part;
           if (pos + 1 == first) {
-            pa += dLd * (T * (c_d - adr));
-            v[ACC_PD] = aT * dLd;
+            pa += T * depth_part;
+            v[ACC_PD] = aTd;
           }
-          v[ACC_PGX] = pa * o * dG_ddelx * ddelx_dx;
-          v[ACC_PGY] = pa * o * dG_ddely * ddely_dy;
+          const float q = pa * G;
+          v[ACC_PGX] = q * dx;  // Q1
+          v[ACC_PGY] = q * dy;  // Q2
         }
       }
-      const float total = warp_reduce16(v, lane);
-      if ((lane & 1) == 0) atomicAdd(acc + (size_t)s_id[j] * kAccStride + (lane >> 1), total);
+      // warp reduction through shared memory: every lane stores its column, 28 lanes each add
+      // half a row (4 x LDS.128), pairs combine with one shuffle, 14 lanes issue one coalesced red
+      float* red = s_red[warp];
+#pragma unroll
+      for (int q = 0; q < kRedVals; ++q) red[q * kRedStride + lane] = v[q];
+      __syncwarp();
+      float sum = 0.f;
+      if (lane < 2 * kRedVals) {
+        const float4* row = reinterpret_cast<const float4*>(red + (lane >> 1) * kRedStride + (lane & 1) * 16);
+        const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+        sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
+              (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (lane < 2 * kRedVals && (lane & 1) == 0)
+        atomicAdd(acc + (size_t)s_id[j] * kAccStride + (lane >> 1), sum);
+      __syncwarp();
     }
   }
 }
