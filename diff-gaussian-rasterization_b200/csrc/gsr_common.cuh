@@ -281,6 +281,39 @@ __device__ __forceinline__ unsigned block_mask8(const float4& r0, const float4& 
   return mask;
 }
 
+// 16-bit mask of the sixteen 4x4-pixel sub-blocks of a 16x16 tile (bit = 4 * block row + block
+// column) that a splat's cut ellipse may touch.  Each half warp of the blend kernels owns one
+// sub-block (see sub_block_of) and walks only the entries whose bit is set.
+__device__ __forceinline__ unsigned block_mask16(const float4& r0, const float4& r1, float tx0,
+                                                 float ty0) {
+  float hx, hy;
+  const int kind = cut_extent(r0.z, r0.w, r1.x, r1.z, hx, hy);
+  if (kind == 0) return 0u;
+  if (kind == 2) return 0xFFFFu;
+  const float x0 = r0.x - hx, x1 = r0.x + hx, y0 = r0.y - hy, y1 = r0.y + hy;
+  unsigned col = 0u, mask = 0u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float bx = tx0 + 4.0f * (float)c;
+    if (x1 >= bx && x0 <= bx + 3.0f) col |= 1u << c;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float by = ty0 + 4.0f * (float)r;
+    if (y1 >= by && y0 <= by + 3.0f) mask |= col << (4 * r);
+  }
+  return mask;
+}
+
+// Pixel <-> thread mapping of the blend kernels: warp w covers the 8x4 block at column (w & 1),
+// row (w >> 1) of the tile; its lower / upper half warp covers the left / right 4x4 sub-block.
+__device__ __forceinline__ void pixel_of_thread(int warp, int lane, int& lx, int& ly, int& sub) {
+  const int half = lane >> 4;
+  lx = (warp & 1) * 8 + half * 4 + (lane & 3);
+  ly = (warp >> 1) * 4 + ((lane >> 2) & 3);
+  sub = (warp >> 1) * 4 + (warp & 1) * 2 + half;  // bit index in block_mask16
+}
+
 __device__ __forceinline__ uint2 pack_rect(uint2 rmin, uint2 rmax) {
   return make_uint2(rmin.x | (rmax.x << 16), rmin.y | (rmax.y << 16));
 }

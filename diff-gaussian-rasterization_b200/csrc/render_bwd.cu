@@ -53,15 +53,18 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ float4 s_r1[kTileThreads];
   __shared__ float4 s_r2[kTileThreads];
   __shared__ int s_id[kTileThreads];
-  __shared__ unsigned char s_mask[kTileThreads];
-  __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];
+  __shared__ unsigned short s_mask[kTileThreads];
+  __shared__ unsigned char s_list[kTileThreads / 16][kTileThreads];
   __shared__ __align__(16) float s_red[kTileThreads / 32][kRedVals * kRedStride];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.y * grid_x + blockIdx.x;
-  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (lane & 7);
-  const int py = blockIdx.y * kTileY + (warp >> 1) * 4 + (lane >> 3);
+  int lx, ly, sub;
+  pixel_of_thread(warp, lane, lx, ly, sub);
+  const int half = lane >> 4;
+  const int px = blockIdx.x * kTileX + lx;
+  const int py = blockIdx.y * kTileY + ly;
   const bool inside = px < W && py < H;
   const uint32_t pix_id = (uint32_t)W * (uint32_t)py + (uint32_t)px;
   const float pixfx = (float)px, pixfy = (float)py;
@@ -108,37 +111,49 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       s_r0[tid] = q0;
       s_r1[tid] = q1;
       s_r2[tid] = __ldg(r + 2);
-      my_mask = block_mask8(q0, q1, tile_x0, tile_y0);
+      my_mask = block_mask16(q0, q1, tile_x0, tile_y0);
     }
-    s_mask[tid] = (unsigned char)my_mask;
+    s_mask[tid] = (unsigned short)my_mask;
     __syncthreads();
 
-    // per-warp compaction: only entries whose cut ellipse can touch this warp's 8x4 block
+    // per-half-warp compaction: only entries whose cut ellipse can touch the half warp's 4x4
+    // pixel block; the two halves walk their own lists side by side
     const int nb = min(kTileThreads, walk - i * kTileThreads);
-    int cnt = 0;
+    const int sub_lo = sub - half, sub_hi = sub_lo + 1;
+    int cnt_lo = 0, cnt_hi = 0;
+    const unsigned lt = (1u << lane) - 1u;
     for (int c = 0; c * 32 < nb; ++c) {
       const int jj = c * 32 + lane;
-      const bool hit = (jj < nb) && ((s_mask[jj] >> warp) & 1u);
-      const unsigned ball = __ballot_sync(0xffffffffu, hit);
-      if (hit) s_list[warp][cnt + __popc(ball & ((1u << lane) - 1u))] = (unsigned char)jj;
-      cnt += __popc(ball);
+      const unsigned m = (jj < nb) ? (unsigned)s_mask[jj] : 0u;
+      const bool hit_lo = (m >> sub_lo) & 1u, hit_hi = (m >> sub_hi) & 1u;
+      const unsigned ball_lo = __ballot_sync(0xffffffffu, hit_lo);
+      const unsigned ball_hi = __ballot_sync(0xffffffffu, hit_hi);
+      if (hit_lo) s_list[2 * warp][cnt_lo + __popc(ball_lo & lt)] = (unsigned char)jj;
+      if (hit_hi) s_list[2 * warp + 1][cnt_hi + __popc(ball_hi & lt)] = (unsigned char)jj;
+      cnt_lo += __popc(ball_lo);
+      cnt_hi += __popc(ball_hi);
     }
     __syncwarp();
-    for (int k = 0; k < cnt; ++k) {
-      const int j = s_list[warp][k];
+    const int cnt = half ? cnt_hi : cnt_lo;
+    const int cnt_max = max(cnt_lo, cnt_hi);
+    const unsigned char* my_list = s_list[2 * warp + half];
+    for (int k = 0; k < cnt_max; ++k) {
+      const bool active = k < cnt;
+      const int j = active ? (int)my_list[k] : 0;
       const int pos = walk - (i * kTileThreads + j) - 1;  // 0-based list position
       const float4 r0 = s_r0[j];
       const float4 r1 = s_r1[j];
       const float dx = GSR_SUB(r0.x, pixfx), dy = GSR_SUB(r0.y, pixfy);
       const float power = pair_power(r0.z, r0.w, r1.x, dx, dy);
-      bool valid = (pos < last_contributor) && !(power > 0.0f) && !(power < r1.z);
+      bool valid = active && (pos < last_contributor) && !(power > 0.0f) && !(power < r1.z);
       float G = 0.f, alpha = 0.f;
       if (valid) {
         G = expf(power);
         alpha = pair_alpha(r1.y, G);
         valid = !(alpha < kAlphaMin);
       }
-      if (!__any_sync(0xffffffffu, valid)) continue;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      if (vmask == 0u) continue;
 
       // Per-pair partial sums.  The screen-space mean, conic and opacity gradients are all moments
       // of w = G * dL/dalpha over (dx, dy); they are summed as moments here and turned into
@@ -219,9 +234,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
               (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
       }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      if (lane < 2 * kRedVals && (lane & 1) == 0)
-        atomicAdd(acc + (size_t)s_id[j] * kAccStride + (lane >> 1), sum);
+      // lane (2q + h) now holds slot q summed over half warp h, i.e. over that half's own entry
+      const int j_lo = __shfl_sync(0xffffffffu, j, 0), j_hi = __shfl_sync(0xffffffffu, j, 16);
+      if (lane < 2 * kRedVals) {
+        const int h = lane & 1;
+        if ((vmask >> (16 * h)) & 0xFFFFu)
+          atomicAdd(acc + (size_t)s_id[h ? j_hi : j_lo] * kAccStride + (lane >> 1), sum);
+      }
       __syncwarp();
     }
   }

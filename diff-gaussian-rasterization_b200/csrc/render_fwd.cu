@@ -40,15 +40,18 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ float4 s_r1[kTileThreads];
   __shared__ float4 s_r2[kTileThreads];
   __shared__ int s_id[kTileThreads];
-  __shared__ unsigned char s_mask[kTileThreads];                    // warp-block mask per entry
-  __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];  // per-warp compacted entries
+  __shared__ unsigned short s_mask[kTileThreads];                      // sub-block mask per entry
+  __shared__ unsigned char s_list[kTileThreads / 16][kTileThreads];    // per-half-warp compacted entries
   __shared__ uint32_t s_red[kTileThreads / 32];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.y * grid_x + blockIdx.x;
-  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (lane & 7);
-  const int py = blockIdx.y * kTileY + (warp >> 1) * 4 + (lane >> 3);
+  int lx, ly, sub;
+  pixel_of_thread(warp, lane, lx, ly, sub);
+  const int half = lane >> 4;
+  const int px = blockIdx.x * kTileX + lx;
+  const int py = blockIdx.y * kTileY + ly;
   const bool inside = px < W && py < H;
   const uint32_t pix_id = (uint32_t)W * (uint32_t)py + (uint32_t)px;
   const float pixfx = (float)px, pixfy = (float)py;
@@ -78,26 +81,36 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       s_r0[tid] = q0;
       s_r1[tid] = q1;
       s_r2[tid] = __ldg(r + 2);
-      my_mask = block_mask8(q0, q1, tile_x0, tile_y0);
+      my_mask = block_mask16(q0, q1, tile_x0, tile_y0);
     }
-    s_mask[tid] = (unsigned char)my_mask;
+    s_mask[tid] = (unsigned short)my_mask;
     __syncthreads();
 
-    // each warp keeps only the entries whose cut ellipse can touch its 8x4 pixel block
+    // each half warp keeps only the entries whose cut ellipse can touch its 4x4 pixel block;
+    // the two halves then walk their own lists side by side
     const int nb = min(kTileThreads, todo);
-    int cnt = 0;
+    int cnt = 0;  // length of this half warp's list
     if (__any_sync(0xffffffffu, !done)) {
+      const int sub_lo = sub - half, sub_hi = sub_lo + 1;
+      int cnt_lo = 0, cnt_hi = 0;
+      const unsigned lt = (1u << lane) - 1u;
       for (int c = 0; c * 32 < nb; ++c) {
         const int j = c * 32 + lane;
-        const bool hit = (j < nb) && ((s_mask[j] >> warp) & 1u);
-        const unsigned ball = __ballot_sync(0xffffffffu, hit);
-        if (hit) s_list[warp][cnt + __popc(ball & ((1u << lane) - 1u))] = (unsigned char)j;
-        cnt += __popc(ball);
+        const unsigned m = (j < nb) ? (unsigned)s_mask[j] : 0u;
+        const bool hit_lo = (m >> sub_lo) & 1u, hit_hi = (m >> sub_hi) & 1u;
+        const unsigned ball_lo = __ballot_sync(0xffffffffu, hit_lo);
+        const unsigned ball_hi = __ballot_sync(0xffffffffu, hit_hi);
+        if (hit_lo) s_list[2 * warp][cnt_lo + __popc(ball_lo & lt)] = (unsigned char)j;
+        if (hit_hi) s_list[2 * warp + 1][cnt_hi + __popc(ball_hi & lt)] = (unsigned char)j;
+        cnt_lo += __popc(ball_lo);
+        cnt_hi += __popc(ball_hi);
       }
       __syncwarp();
+      cnt = half ? cnt_hi : cnt_lo;
     }
+    const unsigned char* my_list = s_list[2 * warp + half];
     for (int k = 0; !done && k < cnt; ++k) {
-      const int j = s_list[warp][k];
+      const int j = my_list[k];
       const uint32_t contributor = (uint32_t)(i * kTileThreads + j + 1);  // 1-based list position
       const float4 r0 = s_r0[j];
       const float4 r1 = s_r1[j];
