@@ -15,7 +15,7 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -178,7 +178,7 @@ int rederive(int variant, int P, int R, int width, int height, char* geom_buffer
     return GSR_E_INVALID;
   }
   GeomState::carve(g, geom_buffer, P, 0);
-  BinState::carve(b, binning_buffer, (size_t)(R > 0 ? R : 0), 0);
+  BinState::carve(b, binning_buffer, (size_t)(R > 0 ? R : 0), 0, false);
   ImgState::carve(img, img_buffer, width * height, cam.grid_x * cam.grid_y, variant);
   return GSR_OK;
 }
@@ -204,6 +204,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "exact_ng")) return &g_opts.exact_ng;
   if (!strcmp(key, "tight_tiles")) return &g_opts.tight_tiles;
   if (!strcmp(key, "stage_timing")) return &g_opts.stage_timing;
+  if (!strcmp(key, "tile_sort")) return &g_opts.tile_sort;
   return nullptr;
 }
 

@@ -44,6 +44,7 @@ struct Options {
   int exact_ng;
   int tight_tiles;
   int stage_timing;
+  int tile_sort;
 };
 Options& options();
 
@@ -127,13 +128,14 @@ struct GeomState {
 };
 
 struct BinState {
-  uint64_t* keys_unsorted;  // [N]
-  uint64_t* keys;           // [N]
-  uint32_t* vals_unsorted;  // [N]
-  uint32_t* vals;           // [N] sorted Gaussian index per (tile, depth) entry
-  char* sort_temp;
+  uint32_t* vals;           // [N] sorted Gaussian index per (tile, depth) entry (always first)
+  uint64_t* keys_unsorted;  // [N] tile-local path: (depth bits << 32 | index) per entry, grouped by tile
+                            //     radix path: (tile << 32 | depth bits)
+  uint64_t* keys;           // [N] radix path only
+  uint32_t* vals_unsorted;  // [N] radix path only
+  char* sort_temp;          //     radix path only
   size_t sort_bytes;
-  static size_t carve(BinState& s, char* base, size_t N, size_t sort_bytes);
+  static size_t carve(BinState& s, char* base, size_t N, size_t sort_bytes, bool radix);
 };
 
 struct ImgState {
@@ -142,6 +144,8 @@ struct ImgState {
   float* final_T;           // [HW] (full only)
   uint32_t* first_contrib;  // [HW] 1-based list position of the first blended entry (full only)
   uint32_t* tile_last;      // [tiles] max n_contrib over the tile's pixels
+  uint32_t* tile_count;     // [tiles] entries per tile (tile-local binning)
+  uint32_t* tile_fill;      // [tiles] scatter cursor per tile
   static size_t carve(ImgState& s, char* base, int HW, int tiles, int variant);
 };
 

@@ -77,6 +77,10 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   alpha >= 15/255 threshold inside the tile (every output is unchanged bit for
  *                   bit; num_rendered is smaller than the reference's); 0: the reference's
  *                   3-sigma rectangle rule, num_rendered identical to the reference.
+ *   "tile_sort"     1 (default): tile-local binning — entries are scattered into their tile's
+ *                   segment and each tile is sorted on chip (same order as the reference's
+ *                   device-wide (tile | depth) radix sort; tiles with more than 8192 entries make
+ *                   the frame fall back to the radix path); 0: always the radix path.
  * Returns the previous value, or GSR_E_INVALID for an unknown key. */
 GSR_API int gsr_set_option(const char* key, int value);
 GSR_API int gsr_get_option(const char* key);

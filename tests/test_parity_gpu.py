@@ -294,6 +294,46 @@ def test_tight_tiles_and_reference_rectangles_give_identical_results(built, vari
         assert rel < 1e-4, (k, rel)
 
 
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_tile_local_binning_equals_radix_binning(built, variant):
+    """The on-chip per-tile sort must give the same entry order as the device-wide radix sort
+    (depth bits, ties by Gaussian index): identical images, n_contrib-dependent gradients equal."""
+    sc, cam, scene = _scene(20000, 320, 240, sig=(1.0, 12.0), seed=43, backdrop=(variant == "full"))
+    # duplicate depths exercise the tie rule
+    m = scene.means3D.clone()
+    m[1000:2000] = m[0:1000]
+    scene = scene._replace(means3D=m)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    o_a, g_a = pu.run_variant(mod, variant, cam, scene, cot)
+    old = pu.set_option("tile_sort", 0)
+    try:
+        o_b, g_b = pu.run_variant(mod, variant, cam, scene, cot)
+    finally:
+        pu.set_option("tile_sort", old)
+    for k in o_a:
+        if k == "gau_uncertainty":
+            assert np.allclose(o_a[k], o_b[k], rtol=1e-5, atol=1e-7)
+        else:
+            assert np.array_equal(o_a[k], o_b[k]), k
+    for k in g_a:
+        rel, _ = pu.grad_mismatch(g_a[k], g_b[k], rtol=1e-4)
+        assert rel < 1e-4, (k, rel)
+
+
+def test_very_long_tile_list_falls_back_to_radix(built):
+    """More than 8192 entries in one tile: the frame takes the radix path and still matches the oracle."""
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(32, 32)
+    scene = sc.make_scene(9000, cam, (3.0, 6.0), seed=44)
+    cot = sc.make_cotangents(cam, 3)
+    mod = built.load_variant("light")
+    outs, grads = pu.run_variant(mod, "light", cam, scene, cot)
+    o_outs, o_grads = pu.run_oracle("light", cam, scene, cot)
+    ok, lines = pu.compare_runs(outs, grads, o_outs, o_grads, flip_budget=5e-3, grad_budget=2e-2)
+    assert ok, "\n".join(lines)
+
+
 # ---- edge cases ----------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("variant", ["light", "full"])
