@@ -158,13 +158,17 @@ int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinS
   if (!img_chunk) { set_error("image allocator returned NULL for %zu bytes", img_need); return GSR_E_ALLOC; }
   ImgState::carve(img, img_chunk, HW, tiles, variant);
 
+  const bool tile_local = options().tile_sort != 0;
   {
-    StageScope st(ST_MEMSET, a.stream);
+    StageScope st(ST_MEMSET, a.stream, 2);
     GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
+    if (tile_local)
+      GSR_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, a.stream));
   }
   int rc = launch_preprocess_fwd(a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations,
                                  a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, cam,
-                                 a.radii, g, a.prefiltered != 0, a.debug != 0, a.stream);
+                                 a.radii, g, tile_local ? img.tile_count : nullptr,
+                                 a.prefiltered != 0, a.debug != 0, a.stream);
   if (rc != GSR_OK) return rc;
   return run_binning(a.P, cam, a.radii, g, a.binning_alloc, a.binning_ctx, b, img, num_rendered,
                      a.debug != 0, a.stream);

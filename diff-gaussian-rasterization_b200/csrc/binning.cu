@@ -126,7 +126,7 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
 // ---- tile-local binning (default path) ---------------------------------------------------------
 // Instead of six HBM passes of a device-wide 45-bit radix sort, entries are scattered straight into
 // their tile's segment and every tile is sorted on chip by one CTA:
-//   count_tiles    one atomic per (Gaussian, tile) duplicate on a per-tile counter
+//   (preprocess_fwd) one red per (Gaussian, tile) duplicate on a per-tile counter
 //   scan_tiles     one CTA: exclusive scan of the tile counters -> ranges, total, longest list
 //   scatter        slot = range.start + atomicAdd(fill[tile]);  entry = depth bits << 32 | index
 //   sort_tiles     one CTA per tile: bitonic sort of the 64-bit entries in shared memory
@@ -136,19 +136,6 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
 // the radix path.
 constexpr int kTileSortCap = 8192;     // entries per tile the shared-memory sort accepts (64 KB)
 constexpr int kTileSortThreads = 256;
-
-__global__ void count_tiles_kernel(int P, const uint32_t* __restrict__ tiles_touched,
-                                   const uint2* __restrict__ rects, int grid_x,
-                                   uint32_t* __restrict__ tile_count) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P) return;
-  if (tiles_touched[idx] == 0) return;
-  const uint2 rc = rects[idx];
-  const uint2 rmin = make_uint2(rc.x & 0xFFFFu, rc.y & 0xFFFFu);
-  const uint2 rmax = make_uint2(rc.x >> 16, rc.y >> 16);
-  for (uint32_t y = rmin.y; y < rmax.y; ++y)
-    for (uint32_t x = rmin.x; x < rmax.x; ++x) atomicAdd(tile_count + y * (uint32_t)grid_x + x, 1u);
-}
 
 // one CTA of 1024 threads; counters[0] = total, counters[2] = longest tile list
 __global__ void __launch_bounds__(1024)
@@ -220,22 +207,79 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
     }
 }
 
-__global__ void __launch_bounds__(kTileSortThreads)
-sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
-                  uint32_t* __restrict__ vals) {
-  extern __shared__ __align__(16) unsigned char sort_smem_raw[];
-  uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem_raw);
-  const uint2 range = ranges[blockIdx.x];
-  const int n = (int)(range.y - range.x);
-  if (n == 0) return;
-  const int tid = threadIdx.x;
-  if (n == 1) {
-    if (tid == 0) vals[range.x] = (uint32_t)entries[range.x];
-    return;
+// Bitonic sort of one tile's entries with E elements per thread held in registers (element index
+// e = m * 256 + tid) over p = 2^LOGP >= n slots.  The network is fully unrolled (j, k are compile
+// time constants); compare-exchange partners at distance j are reached with warp shuffles
+// (j < 32), through shared memory (32 <= j < 256) or inside the thread (j >= 256), so only 6 of
+// the 36 steps of a 256-entry tile need a barrier.  Threads beyond p leave at once.
+__device__ __forceinline__ uint64_t cex_pick(uint64_t a, uint64_t o, bool keep_min) {
+  const bool a_lt = a < o;
+  return (a_lt == keep_min) ? a : o;
+}
+
+template <int E, int LOGP>
+__device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, const uint64_t* __restrict__ entries,
+                                                  uint32_t* __restrict__ out, int n, int tid) {
+  constexpr int T = kTileSortThreads;
+  if (E == 1 && tid >= ((1 << LOGP) < 32 ? 32 : (1 << LOGP))) return;  // whole idle warps leave
+  uint64_t v[E];
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int e = m * T + tid;
+    v[m] = (e < n) ? entries[e] : ~0ull;
   }
+#pragma unroll
+  for (int lk = 1; lk <= LOGP; ++lk) {
+    const int k = 1 << lk;
+#pragma unroll
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
+      if (j >= T) {
+        const int JM = j / T;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          if ((m & JM) == 0 && (m | JM) < E) {
+            const bool up = ((m * T + tid) & k) == 0;
+            const uint64_t a = v[m], b = v[m | JM];
+            const bool sw = (a > b) == up;
+            v[m] = sw ? b : a;
+            v[m | JM] = sw ? a : b;
+          }
+        }
+      } else if (j >= 32) {
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < E; ++m) s[m * T + tid] = v[m];
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const int e = m * T + tid;
+          const bool keep_min = ((e & j) == 0) == ((e & k) == 0);
+          v[m] = cex_pick(v[m], s[e ^ j], keep_min);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const int e = m * T + tid;
+          const bool keep_min = ((e & j) == 0) == ((e & k) == 0);
+          v[m] = cex_pick(v[m], __shfl_xor_sync(0xffffffffu, v[m], j), keep_min);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int e = m * T + tid;
+    if (e < n) out[e] = (uint32_t)v[m];
+  }
+}
+
+// generic shared-memory network for long lists (2048 < n <= kTileSortCap)
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, const uint64_t* __restrict__ entries,
+                                                  uint32_t* __restrict__ out, int n, int tid) {
   int p = 2;
   while (p < n) p <<= 1;
-  for (int i = tid; i < p; i += kTileSortThreads) s[i] = (i < n) ? entries[range.x + i] : ~0ull;
+  for (int i = tid; i < p; i += kTileSortThreads) s[i] = (i < n) ? entries[i] : ~0ull;
   __syncthreads();
   for (int k = 2; k <= p; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -249,7 +293,36 @@ sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__
       __syncthreads();
     }
   }
-  for (int i = tid; i < n; i += kTileSortThreads) vals[range.x + i] = (uint32_t)s[i];
+  for (int i = tid; i < n; i += kTileSortThreads) out[i] = (uint32_t)s[i];
+}
+
+__global__ void __launch_bounds__(kTileSortThreads)
+sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
+                  uint32_t* __restrict__ vals) {
+  extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+  uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem_raw);
+  const uint2 range = ranges[blockIdx.x];
+  const int n = (int)(range.y - range.x);
+  if (n == 0) return;
+  const int tid = threadIdx.x;
+  const uint64_t* in = entries + range.x;
+  uint32_t* out = vals + range.x;
+  if (n == 1) {
+    if (tid == 0) out[0] = (uint32_t)in[0];
+  } else if (n <= 2) { bitonic_sort_regs<1, 1>(s, in, out, n, tid);
+  } else if (n <= 4) { bitonic_sort_regs<1, 2>(s, in, out, n, tid);
+  } else if (n <= 8) { bitonic_sort_regs<1, 3>(s, in, out, n, tid);
+  } else if (n <= 16) { bitonic_sort_regs<1, 4>(s, in, out, n, tid);
+  } else if (n <= 32) { bitonic_sort_regs<1, 5>(s, in, out, n, tid);
+  } else if (n <= 64) { bitonic_sort_regs<1, 6>(s, in, out, n, tid);
+  } else if (n <= 128) { bitonic_sort_regs<1, 7>(s, in, out, n, tid);
+  } else if (n <= 256) { bitonic_sort_regs<1, 8>(s, in, out, n, tid);
+  } else if (n <= 512) { bitonic_sort_regs<2, 9>(s, in, out, n, tid);
+  } else if (n <= 1024) { bitonic_sort_regs<4, 10>(s, in, out, n, tid);
+  } else if (n <= 2048) { bitonic_sort_regs<8, 11>(s, in, out, n, tid);
+  } else {
+    bitonic_sort_smem(s, in, out, n, tid);
+  }
 }
 
 }  // namespace
@@ -263,14 +336,8 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
 
   if (tile_local) {
     {
-      StageScope st(ST_MEMSET, stream);
-      GSR_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, stream));
-    }
-    {
-      StageScope st(ST_SCAN, stream, 2);
-      count_tiles_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.tiles_touched, g.rect, cam.grid_x,
-                                                               img.tile_count);
-      GSR_LAUNCH_OK(debug, stream);
+      // img.tile_count was filled by preprocess_fwd (one red per duplicate)
+      StageScope st(ST_SCAN, stream, 1);
       scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
                                                 g.counters);
       GSR_LAUNCH_OK(debug, stream);
@@ -316,7 +383,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     }
     {
       StageScope st(ST_SORT, stream);
-      int p = 2;
+      int p = kTileSortThreads;  // the register network exchanges 256*E entries through smem
       while (p < (int)longest) p <<= 1;
       const size_t smem = (size_t)p * sizeof(uint64_t);
       static bool attr_set = false;

@@ -348,7 +348,8 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
                           float scale_modifier, const float* rotations, const float* opacities,
                           const float* shs, const float* cov3D_precomp,
                           const float* colors_precomp, const Camera& cam, int* radii,
-                          GeomState& g, bool prefiltered, bool debug, cudaStream_t stream);
+                          GeomState& g, uint32_t* tile_count /* zeroed, or NULL */, bool prefiltered,
+                          bool debug, cudaStream_t stream);
 
 int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_alloc_fn alloc,
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,

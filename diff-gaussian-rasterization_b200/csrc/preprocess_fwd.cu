@@ -173,7 +173,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int H, float tanx, float tany, float fx, float fy, int grid_x, int grid_y,
                       int* __restrict__ radii, float4* __restrict__ rec, float* __restrict__ cov3Ds,
                       unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                      uint2* __restrict__ rects, bool prefiltered, bool tight_tiles) {
+                      uint2* __restrict__ rects, uint32_t* __restrict__ tile_count,
+                      bool prefiltered, bool tight_tiles) {
   extern __shared__ float sh_smem[];  // [kPreThreads][M*3+1] when shs != nullptr
   const int base = blockIdx.x * kPreThreads;
   const int idx = base + threadIdx.x;
@@ -287,6 +288,10 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     }
     my_tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
     my_rect = pack_rect(rmin, rmax);
+    if (tile_count != nullptr) {  // tile-local binning: per-tile entry counters (fire-and-forget reds)
+      for (uint32_t y = rmin.y; y < rmax.y; ++y)
+        for (uint32_t x = rmin.x; x < rmax.x; ++x) atomicAdd(tile_count + y * (uint32_t)grid_x + x, 1u);
+    }
     rec[3 * (size_t)idx + 0] = make_float4(pix.x, pix.y, conic.x, conic.y);
     rec[3 * (size_t)idx + 1] = make_float4(conic.z, opacity, power_cut, p_view.z);
     rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
@@ -313,7 +318,8 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
                           float scale_modifier, const float* rotations, const float* opacities,
                           const float* shs, const float* cov3D_precomp,
                           const float* colors_precomp, const Camera& cam, int* radii,
-                          GeomState& g, bool prefiltered, bool debug, cudaStream_t stream) {
+                          GeomState& g, uint32_t* tile_count, bool prefiltered, bool debug,
+                          cudaStream_t stream) {
   if (colors_precomp == nullptr && (shs == nullptr || M <= 0 || M > kMaxCoeffs)) {
     set_error("SH colours need 1 <= M <= %d coefficients (got %d)", kMaxCoeffs, M);
     return GSR_E_INVALID;
@@ -330,7 +336,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,
       cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,
-      g.tiles_touched, g.rect, prefiltered, options().tight_tiles != 0);
+      g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0);
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
 }
