@@ -323,6 +323,8 @@ def main():
     if world > 1:
         dp = ge.load_dp_module()
         reducer = dp.SceneGradReducer({k: tuple(v.shape) for k, v in frame.params.items()}, device)
+        zero_copy = reducer.attach(mod)   # B200 arm: backward writes into the flat buffer directly
+        log("rank %d: gradient arena attached: %s" % (rank, zero_copy))
 
     lib = None
     if a.impl == "b200":

@@ -44,6 +44,40 @@ torch::Tensor scratch_for(int P, const torch::TensorOptions& fopts) {
   return torch::empty({static_cast<long long>(gsr_backward_scratch_floats(P))}, fopts);
 }
 
+torch::Tensor g_grad_arena;  // see setGradArena
+
+struct SceneGrads {
+  torch::Tensor means3D, sh, opacity, scales, rotations;
+};
+
+// the five scene-parameter gradients: views of the registered arena when it fits, fresh tensors otherwise
+SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torch::TensorOptions& fopts) {
+  SceneGrads g;
+  const int64_t need = (int64_t)P * (3 + 3 * (int64_t)M + 1 + 3 + 4);
+  if (g_grad_arena.defined() && g_grad_arena.numel() == need && g_grad_arena.device() == like.device() &&
+      g_grad_arena.scalar_type() == torch::kFloat32 && g_grad_arena.is_contiguous() && P > 0 &&
+      P % 4 == 0 /* keeps every slice 16-byte aligned for the kernels' 128-bit stores */) {
+    int64_t off = 0;
+    auto take = [&](int64_t n, std::vector<int64_t> shape) {
+      torch::Tensor t = g_grad_arena.narrow(0, off, n).view(shape);
+      off += n;
+      return t;
+    };
+    g.means3D = take((int64_t)P * 3, {P, 3});
+    g.sh = take((int64_t)P * M * 3, {P, M, 3});
+    g.opacity = take((int64_t)P, {P, 1});
+    g.scales = take((int64_t)P * 3, {P, 3});
+    g.rotations = take((int64_t)P * 4, {P, 4});
+  } else {
+    g.means3D = torch::empty({P, 3}, fopts);
+    g.sh = torch::empty({P, M, 3}, fopts);
+    g.opacity = torch::empty({P, 1}, fopts);
+    g.scales = torch::empty({P, 3}, fopts);
+    g.rotations = torch::empty({P, 4}, fopts);
+  }
+  return g;
+}
+
 }  // namespace
 
 #if defined(GSR_VARIANT_LIGHT)
@@ -133,16 +167,17 @@ RasterizeGaussiansBackwardCUDA(
   if (sh.size(0) != 0) M = sh.size(1);
   auto fopts = means3D.options().dtype(torch::kFloat32);
 
-  torch::Tensor dL_dmeans3D = torch::empty({P, 3}, fopts);
+  SceneGrads sg = alloc_scene_grads(P, M, means3D, fopts);
+  torch::Tensor dL_dmeans3D = sg.means3D;
   torch::Tensor dL_dmeans2D = torch::empty({P, 3}, fopts);
   torch::Tensor dL_dcolors = torch::empty({P, 3}, fopts);
   torch::Tensor dL_ddepths = torch::empty({P, 1}, fopts);
   torch::Tensor dL_dconic = torch::empty({P, 2, 2}, fopts);
-  torch::Tensor dL_dopacity = torch::empty({P, 1}, fopts);
+  torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
-  torch::Tensor dL_dsh = torch::empty({P, M, 3}, fopts);
-  torch::Tensor dL_dscales = torch::empty({P, 3}, fopts);
-  torch::Tensor dL_drotations = torch::empty({P, 4}, fopts);
+  torch::Tensor dL_dsh = sg.sh;
+  torch::Tensor dL_dscales = sg.scales;
+  torch::Tensor dL_drotations = sg.rotations;
   torch::Tensor dL_dview = torch::empty({1, 4, 4}, fopts);
   torch::Tensor scratch = scratch_for(P, fopts);
 
@@ -252,16 +287,17 @@ RasterizeGaussiansBackwardCUDA(
   if (sh.size(0) != 0) M = sh.size(1);
   auto fopts = means3D.options().dtype(torch::kFloat32);
 
-  torch::Tensor dL_dmeans3D = torch::empty({P, 3}, fopts);
+  SceneGrads sg = alloc_scene_grads(P, M, means3D, fopts);
+  torch::Tensor dL_dmeans3D = sg.means3D;
   torch::Tensor dL_dmeans2D = torch::empty({P, 3}, fopts);
   torch::Tensor dL_dcolors = torch::empty({P, 3}, fopts);
   torch::Tensor dL_dgau_depths = torch::empty({P, 1}, fopts);
   torch::Tensor dL_dconic = torch::empty({P, 2, 2}, fopts);
-  torch::Tensor dL_dopacity = torch::empty({P, 1}, fopts);
+  torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
-  torch::Tensor dL_dsh = torch::empty({P, M, 3}, fopts);
-  torch::Tensor dL_dscales = torch::empty({P, 3}, fopts);
-  torch::Tensor dL_drotations = torch::empty({P, 4}, fopts);
+  torch::Tensor dL_dsh = sg.sh;
+  torch::Tensor dL_dscales = sg.scales;
+  torch::Tensor dL_drotations = sg.rotations;
   torch::Tensor dL_dview = torch::empty({4, 4}, fopts);
   torch::Tensor scratch = scratch_for(P, fopts);
 
@@ -294,6 +330,17 @@ RasterizeGaussiansBackwardCUDA(
 }
 
 #endif
+
+void setGradArena(const torch::Tensor& arena) {
+  if (!arena.defined() || arena.numel() == 0) {
+    g_grad_arena = torch::Tensor();
+    return;
+  }
+  TORCH_CHECK(arena.is_cuda() && arena.scalar_type() == torch::kFloat32 && arena.is_contiguous() &&
+                  arena.dim() == 1,
+              "grad arena must be a contiguous 1-D float32 CUDA tensor");
+  g_grad_arena = arena;
+}
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,
                           torch::Tensor& projmatrix) {

@@ -68,5 +68,12 @@ RasterizeGaussiansBackwardCUDA(
 #error "define GSR_VARIANT_LIGHT or GSR_VARIANT_FULL"
 #endif
 
+// Registers (or clears, with an undefined / empty tensor) a flat fp32 CUDA buffer of
+// P*(3 + 3M + 1 + 3 + 4) floats laid out [means3D | sh | opacity | scales | rotations].  While it is
+// registered and its size matches, RasterizeGaussiansBackwardCUDA writes those five gradients
+// straight into it (the returned tensors are views), so a data-parallel caller can all-reduce one
+// buffer without packing.  Not part of the reference surface.
+void setGradArena(const torch::Tensor& arena);
+
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,
                           torch::Tensor& projmatrix);

@@ -56,10 +56,36 @@ class SceneGradReducer:
             g = grads[k]
             self.flat[o:o + n].copy_(g.reshape(-1) if g is not None else 0)
 
+    def attach(self, rasterizer_module):
+        """Register the flat buffer as the gradient arena of a B200-native rasterizer package
+        (`_C.set_grad_arena`): its backward then writes the five scene gradients straight into
+        the buffer and reduce_async() needs no packing copy.  Returns False (and changes nothing)
+        for packages without that extension, e.g. the reference build."""
+        fn = getattr(getattr(rasterizer_module, "_C", None), "set_grad_arena", None)
+        if fn is None or not self.is_cuda:
+            return False
+        fn(self.flat)
+        self._attached = rasterizer_module
+        return True
+
+    def detach(self):
+        mod = getattr(self, "_attached", None)
+        if mod is not None:
+            mod._C.set_grad_arena(torch.Tensor())
+            self._attached = None
+
+    def _aliases_flat(self, grads):
+        lo = self.flat.data_ptr()
+        for k, (o, _n, _shape) in self.slices.items():
+            g = grads.get(k)
+            if g is None or g.data_ptr() != lo + 4 * o:
+                return False
+        return True
+
     def reduce_async(self, grads=None):
-        """Pack (unless the gradients were written into views() directly) and launch the single
-        all-reduce.  Returns immediately; call wait() before reading views()."""
-        if grads is not None:
+        """Pack (unless the gradients already live in the flat buffer, see attach()) and launch
+        the single all-reduce.  Returns immediately; call wait() before reading views()."""
+        if grads is not None and not self._aliases_flat(grads):
             self.pack(grads)
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             self._work = None

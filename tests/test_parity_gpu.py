@@ -508,3 +508,32 @@ def test_render_helper_matches_direct_rasterizer_call(built, variant):
     assert rel < 1e-3
     rel, _ = pu.grad_mismatch(g.get_xyz.grad.cpu().numpy(), ref_g["means3D"])
     assert rel < 1e-3
+
+
+# ---- flat gradient arena (view-level data parallelism, zero-copy) --------------------------------
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_grad_arena_receives_scene_gradients(built, variant):
+    sc, cam, scene = _scene(2000, 160, 96, seed=61)   # P % 4 == 0
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    dp = ge.load_dp_module()
+    _, ref = pu.run_variant(mod, variant, cam, scene, cot)
+    shapes = dict(means3D=(2000, 3), shs=(2000, 16, 3), opacities=(2000, 1), scales=(2000, 3), rotations=(2000, 4))
+    red = dp.SceneGradReducer(shapes, DEV)
+    assert red.attach(mod)
+    try:
+        _, got = pu.run_variant(mod, variant, cam, scene, cot)
+        torch.cuda.synchronize()
+        views = red.wait()
+        for k in shapes:
+            rel, _ = pu.grad_mismatch(views[k].cpu().numpy(), ref[k], rtol=1e-4)
+            assert rel < 1e-4, k
+            rel, _ = pu.grad_mismatch(got[k], ref[k], rtol=1e-4)
+            assert rel < 1e-4, k
+    finally:
+        red.detach()
+    # detached: the arena is no longer written
+    red.flat.zero_()
+    pu.run_variant(mod, variant, cam, scene, cot)
+    assert float(red.flat.abs().max()) == 0.0
