@@ -261,7 +261,18 @@ def oracle_threads():
     return (os.cpu_count() or 1) if omp else 1
 
 
+def _private_stdout():
+    """Keep the real stdout for the ONE JSON line and point fd 1 at stderr for everything else
+    (NCCL and other libraries print banners to stdout)."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
 def main():
+    out_stream = _private_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -298,7 +309,7 @@ def main():
         fps, dt = cpu_oracle_sample(ge, a.config, a.variant, frames)
         cores = oracle_threads()
         sample = "%d full frames of the workload through the CPU oracle port (fwd+bwd), %.1f s" % (frames, dt)
-        print(json.dumps({
+        print(file=out_stream, flush=True, *[json.dumps({
             "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus,
             "steps": frames, "warmup": 0, "ms_per_step": 1000.0 / fps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -306,7 +317,7 @@ def main():
                        "the reference has no CPU path, this is the oracle port"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})])
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
@@ -465,7 +476,7 @@ def main():
             out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": oracle_threads(), "kind": "port",
                                    "sample": "%d full frames of the workload (fwd+bwd) through the CPU oracle, "
                                              "%.1f s; the reference has no CPU implementation" % (a.cpu_frames, dt)}
-    print(json.dumps(out))
+    print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
