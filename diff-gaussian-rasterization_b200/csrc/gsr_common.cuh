@@ -45,6 +45,7 @@ struct Options {
   int tight_tiles;
   int stage_timing;
   int tile_sort;
+  int bwd_packed;
 };
 Options& options();
 

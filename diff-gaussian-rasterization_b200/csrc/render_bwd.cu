@@ -246,6 +246,285 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   }
 }
 
+
+// =================================================================================================
+// Packed variant (default): 128 threads per tile, every lane owns TWO vertically adjacent pixels and
+// does their arithmetic with Blackwell's packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2: one
+// issue slot for two lanes of work — the blend kernels are issue-bound, not FMA-pipe bound).
+// A warp covers an 8x8 pixel block, so an entry is visited by fewer warps than with 8x4 blocks,
+// and the per-entry fixed costs (staging reads, cull vote, reduction, atomics) are paid per 64
+// pixels instead of per 32.
+//  * per-entry data is staged in shared memory already duplicated into (v, v) pairs, so that the
+//    packed operands come straight out of LDS.128;
+//  * the per-pixel state uses the compositing recurrence  B <- B + alpha (c - B)  ("colour behind
+//    the current entry"), which is branch-free for pixels the entry does not touch (alpha = G = 0
+//    leaves T and B unchanged and makes every partial sum exactly zero);
+//  * power / alpha are evaluated with the same rounding sequence as the forward (packed ops are
+//    IEEE round-to-nearest per element), so both passes take identical skip decisions.
+// =================================================================================================
+typedef unsigned long long f2;  // two packed floats (lo = pixel row y0, hi = pixel row y0 + 1)
+
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(f2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float f2_hi(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+constexpr int kBwd2Threads = 128;
+constexpr int kBwd2Warps = kBwd2Threads / 32;
+constexpr int kBwd2Batch = 128;  // entries staged per round (one per thread)
+
+// 4-bit mask of the four 8x8 pixel blocks of a tile (bit = 2 * block row + block column)
+__device__ __forceinline__ unsigned block_mask4(const float4& r0, const float4& r1, float tx0, float ty0) {
+  float hx, hy;
+  const int kind = cut_extent(r0.z, r0.w, r1.x, r1.z, hx, hy);
+  if (kind == 0) return 0u;
+  if (kind == 2) return 0xFu;
+  const float x0 = r0.x - hx, x1 = r0.x + hx, y0 = r0.y - hy, y1 = r0.y + hy;
+  const unsigned col = ((x1 >= tx0 && x0 <= tx0 + 7.0f) ? 1u : 0u) |
+                       ((x1 >= tx0 + 8.0f && x0 <= tx0 + 15.0f) ? 2u : 0u);
+  unsigned mask = 0u;
+  if (y1 >= ty0 && y0 <= ty0 + 7.0f) mask |= col;
+  if (y1 >= ty0 + 8.0f && y0 <= ty0 + 15.0f) mask |= col << 2;
+  return mask;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kBwd2Threads)
+render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
+                   const float4* __restrict__ rec, const float* __restrict__ bg,
+                   const float* __restrict__ gt_depth,
+                   const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
+                   const float* __restrict__ final_Ts,    // full
+                   const uint32_t* __restrict__ n_contrib,
+                   const uint32_t* __restrict__ first_contrib,  // full
+                   const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepths,
+                   const float* __restrict__ dL_dmedians,  // light
+                   const float* __restrict__ dL_dvars,     // light: depth_var, full: uncertainty
+                   float* __restrict__ acc) {
+  // staged entry, duplicated into pairs: q0 = (xg, pc | yg, yg)  q1 = (A, A | -B, -B)
+  //   q2 = (C, C | o, o)  q3 = (depth, depth | r, r)  q4 = (g, g | b, b)
+  __shared__ ulonglong2 s_q0[kBwd2Batch], s_q1[kBwd2Batch], s_q2[kBwd2Batch], s_q3[kBwd2Batch],
+      s_q4[kBwd2Batch];
+  __shared__ int s_id[kBwd2Batch];
+  __shared__ unsigned char s_mask[kBwd2Batch];
+  __shared__ unsigned char s_list[kBwd2Warps][kBwd2Batch];
+  __shared__ __align__(16) float s_red[kBwd2Warps][kRedVals * kRedStride];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
+  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (lane & 7);
+  const int py0 = blockIdx.y * kTileY + (warp >> 1) * 8 + 2 * (lane >> 3);
+  const int py1 = py0 + 1;
+  const bool in_a = px < W && py0 < H, in_b = px < W && py1 < H;
+  const uint32_t pix_a = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
+  const uint32_t pix_b = pix_a + (uint32_t)W;
+  const float pxf = (float)px;
+  const f2 npy2 = f2_pack(-(float)py0, -(float)py1);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
+
+  const uint2 range = ranges[tile];
+  const int walk = (int)tile_last[tile];  // entries [0, walk) were used by some pixel
+  const int rounds = (walk + kBwd2Batch - 1) / kBwd2Batch;
+  const size_t HW = (size_t)H * (size_t)W;
+
+  // per-pixel constants and state, packed (a, b)
+  float Tf_a = 0.f, Tf_b = 0.f, g0a = 0.f, g0b = 0.f, g1a = 0.f, g1b = 0.f, g2a = 0.f, g2b = 0.f;
+  float gda = 0.f, gdb = 0.f, gva = 0.f, gvb = 0.f, gta = 0.f, gtb = 0.f, gma = 0.f, gmb = 0.f;
+  int lc_a = 0, lc_b = 0, first_a = 0, first_b = 0;
+  if (in_a) {
+    Tf_a = (VARIANT == kLight) ? (1 - alphas[pix_a]) : final_Ts[pix_a];
+    lc_a = (int)n_contrib[pix_a];
+    g0a = dL_dpix[pix_a]; g1a = dL_dpix[HW + pix_a]; g2a = dL_dpix[2 * HW + pix_a];
+    gda = dL_ddepths[pix_a]; gva = dL_dvars[pix_a]; gta = gt_depth[pix_a];
+    if (VARIANT == kLight) gma = dL_dmedians[pix_a];
+    if (VARIANT == kFull) first_a = (int)first_contrib[pix_a];
+  }
+  if (in_b) {
+    Tf_b = (VARIANT == kLight) ? (1 - alphas[pix_b]) : final_Ts[pix_b];
+    lc_b = (int)n_contrib[pix_b];
+    g0b = dL_dpix[pix_b]; g1b = dL_dpix[HW + pix_b]; g2b = dL_dpix[2 * HW + pix_b];
+    gdb = dL_ddepths[pix_b]; gvb = dL_dvars[pix_b]; gtb = gt_depth[pix_b];
+    if (VARIANT == kLight) gmb = dL_dmedians[pix_b];
+    if (VARIANT == kFull) first_b = (int)first_contrib[pix_b];
+  }
+  const f2 Tf2 = f2_pack(Tf_a, Tf_b);
+  const f2 dLp0 = f2_pack(g0a, g0b), dLp1 = f2_pack(g1a, g1b), dLp2 = f2_pack(g2a, g2b);
+  const f2 dLd = f2_pack(gda, gdb), dLv = f2_pack(gva, gvb), dLv_x2 = f2_pack(2.f * gva, 2.f * gvb);
+  const f2 ngt2 = f2_pack(-gta, -gtb);
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  const f2 nbgdot = f2_pack(-(bg0 * g0a + bg1 * g1a + bg2 * g2a), -(bg0 * g0b + bg1 * g1b + bg2 * g2b));
+  const f2 one2 = f2_pack(1.f, 1.f), mone2 = f2_pack(-1.f, -1.f), mhalf2 = f2_pack(-0.5f, -0.5f);
+  f2 T2 = Tf2;
+  f2 Bc0 = 0ull, Bc1 = 0ull, Bc2 = 0ull, Bd = 0ull, Bv = 0ull;  // colour / depth / var "behind" the entry
+  bool mid_a = true, mid_b = true;
+
+  for (int i = 0; i < rounds; ++i) {
+    __syncthreads();
+    const int progress = i * kBwd2Batch + tid;
+    unsigned my_mask = 0u;
+    if (progress < walk) {
+      const int id = (int)point_list[range.x + (walk - progress - 1)];
+      s_id[tid] = id;
+      const float4* r = rec + 3 * (size_t)id;
+      const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+      my_mask = block_mask4(q0, q1, tile_x0, tile_y0);
+      s_q0[tid] = make_ulonglong2(f2_pack(q0.x, q1.z), f2_pack(q0.y, q0.y));
+      s_q1[tid] = make_ulonglong2(f2_pack(q0.z, q0.z), f2_pack(-q0.w, -q0.w));
+      s_q2[tid] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q1.y));
+      s_q3[tid] = make_ulonglong2(f2_pack(q1.w, q1.w), f2_pack(q2.x, q2.x));
+      s_q4[tid] = make_ulonglong2(f2_pack(q2.y, q2.y), f2_pack(q2.z, q2.z));
+    }
+    s_mask[tid] = (unsigned char)my_mask;
+    __syncthreads();
+
+    // per-warp compaction: only entries whose cut ellipse can touch this warp's 8x8 block
+    const int nb = min(kBwd2Batch, walk - i * kBwd2Batch);
+    int cnt = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c = 0; c * 32 < nb; ++c) {
+      const int jj = c * 32 + lane;
+      const bool hit = (jj < nb) && ((s_mask[jj] >> warp) & 1u);
+      const unsigned ball = __ballot_sync(0xffffffffu, hit);
+      if (hit) s_list[warp][cnt + __popc(ball & lt)] = (unsigned char)jj;
+      cnt += __popc(ball);
+    }
+    __syncwarp();
+
+    for (int k = 0; k < cnt; ++k) {
+      const int j = s_list[warp][k];
+      const int pos = walk - (i * kBwd2Batch + j) - 1;  // 0-based list position
+      const ulonglong2 e0 = s_q0[j], e1 = s_q1[j], e2 = s_q2[j];
+      const float dx = GSR_SUB(f2_lo(e0.x), pxf);
+      const float pc = f2_hi(e0.x);
+      const f2 dx2 = f2_pack(dx, dx);
+      const f2 dy2 = f2_add(e0.y, npy2);
+      // pair_power for both pixels, same rounding sequence as the scalar version:
+      //   fma(fma(dx, dx*A, dy*(dy*C)), -0.5, -(dy*(dx*B)))
+      const f2 qf = f2_fma(dx2, f2_mul(dx2, e1.x), f2_mul(dy2, f2_mul(dy2, e2.x)));
+      const f2 pw2 = f2_fma(qf, mhalf2, f2_mul(dy2, f2_mul(dx2, e1.y)));
+      const float pw_a = f2_lo(pw2), pw_b = f2_hi(pw2);
+      bool va = (pos < lc_a) && !(pw_a > 0.0f) && !(pw_a < pc);
+      bool vb = (pos < lc_b) && !(pw_b > 0.0f) && !(pw_b < pc);
+      if (!__any_sync(0xffffffffu, va || vb)) continue;
+      const float o = f2_lo(e2.y);
+      float Ga = 0.f, Gb = 0.f, al_a = 0.f, al_b = 0.f;
+      if (va) {
+        Ga = expf(pw_a);
+        al_a = pair_alpha(o, Ga);
+        va = !(al_a < kAlphaMin);
+      }
+      if (vb) {
+        Gb = expf(pw_b);
+        al_b = pair_alpha(o, Gb);
+        vb = !(al_b < kAlphaMin);
+      }
+      if (!__any_sync(0xffffffffu, va || vb)) continue;
+      if (!va) { Ga = 0.f; al_a = 0.f; }
+      if (!vb) { Gb = 0.f; al_b = 0.f; }
+      const f2 G2 = f2_pack(Ga, Gb), alpha2 = f2_pack(al_a, al_b);
+
+      const ulonglong2 e3 = s_q3[j], e4 = s_q4[j];
+      const f2 om2 = f2_fma(alpha2, mone2, one2);  // 1 - alpha (>= 0.01)
+      const f2 inv2 = f2_pack(fast_rcp(f2_lo(om2)), fast_rcp(f2_hi(om2)));
+      T2 = f2_mul(T2, inv2);
+      const f2 aT2 = f2_mul(alpha2, T2);
+      // c - B for colour, depth and var
+      const f2 d0 = f2_fma(Bc0, mone2, e3.y), d1 = f2_fma(Bc1, mone2, e4.x), d2 = f2_fma(Bc2, mone2, e4.y);
+      const f2 dgt2 = f2_add(e3.x, ngt2);
+      const f2 cvar2 = f2_mul(dgt2, dgt2);
+      const f2 dd = f2_fma(Bd, mone2, e3.x), dv = f2_fma(Bv, mone2, cvar2);
+      const f2 colour_part = f2_fma(d2, dLp2, f2_fma(d1, dLp1, f2_mul(d0, dLp0)));
+      const f2 depth_part = f2_mul(dd, dLd);
+      f2 dLa = f2_fma(dv, dLv, f2_add(colour_part, depth_part));
+      // B <- B + alpha (c - B)
+      Bc0 = f2_fma(alpha2, d0, Bc0);
+      Bc1 = f2_fma(alpha2, d1, Bc1);
+      Bc2 = f2_fma(alpha2, d2, Bc2);
+      Bd = f2_fma(alpha2, dd, Bd);
+      Bv = f2_fma(alpha2, dv, Bv);
+      const f2 aTd = f2_mul(aT2, dLd);
+      // dL/dalpha = T * (...) - T_final / (1 - alpha) * (bg . dL/dpixel)
+      dLa = f2_fma(f2_mul(Tf2, inv2), nbgdot, f2_mul(dLa, T2));
+      const f2 w2 = f2_mul(G2, dLa);
+      const f2 wx = f2_mul(w2, dx2), wy = f2_mul(w2, dy2);
+
+      f2 v[kRedVals];
+      v[ACC_MX] = wx;
+      v[ACC_MY] = wy;
+      v[ACC_CA] = f2_mul(wx, dx2);
+      v[ACC_CB] = f2_mul(wx, dy2);
+      v[ACC_CC] = f2_mul(wy, dy2);
+      v[ACC_OP] = w2;
+      v[ACC_R] = f2_mul(aT2, dLp0);
+      v[ACC_G] = f2_mul(aT2, dLp1);
+      v[ACC_B] = f2_mul(aT2, dLp2);
+      v[ACC_DEPTH] = f2_fma(f2_mul(aT2, dgt2), dLv_x2, aTd);
+      v[ACC_PGX] = 0ull;
+      v[ACC_PGY] = 0ull;
+      v[ACC_PD] = 0ull;
+      v[ACC_MED] = 0ull;
+      if (VARIANT == kLight) {
+        v[ACC_PD] = aTd;
+        // median: the first valid entry met from the back whose restored T exceeds 0.5
+        float med_a = 0.f, med_b = 0.f;
+        if (va && mid_a && f2_lo(T2) > 0.5f) { med_a = gma; mid_a = false; }
+        if (vb && mid_b && f2_hi(T2) > 0.5f) { med_b = gmb; mid_b = false; }
+        v[ACC_MED] = f2_pack(med_a, med_b);
+      } else {
+        // pose terms of the reference's ComputePG: colour through ndc without the background
+        // term (full backward.cu:746-777, :1028-1072); depth only from the front-most valid
+        // contributor of the pixel, because dd_dv* is assigned, not accumulated (:1278-1289).
+        const bool fa = va && (pos + 1 == first_a), fb = vb && (pos + 1 == first_b);
+        const f2 fsel = f2_pack(fa ? 1.f : 0.f, fb ? 1.f : 0.f);
+        const f2 pa = f2_mul(T2, f2_fma(fsel, depth_part, colour_part));
+        v[ACC_PD] = f2_mul(fsel, aTd);
+        const f2 q = f2_mul(pa, G2);
+        v[ACC_PGX] = f2_mul(q, dx2);
+        v[ACC_PGY] = f2_mul(q, dy2);
+      }
+      // warp reduction through shared memory (both pixels of a lane are added first)
+      float* red = s_red[warp];
+#pragma unroll
+      for (int qn = 0; qn < kRedVals; ++qn) red[qn * kRedStride + lane] = f2_lo(v[qn]) + f2_hi(v[qn]);
+      __syncwarp();
+      float sum = 0.f;
+      if (lane < 2 * kRedVals) {
+        const float4* row = reinterpret_cast<const float4*>(red + (lane >> 1) * kRedStride + (lane & 1) * 16);
+        const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+        sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
+              (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (lane < 2 * kRedVals && (lane & 1) == 0)
+        atomicAdd(acc + (size_t)s_id[j] * kAccStride + (lane >> 1), sum);
+      __syncwarp();
+    }
+  }
+}
+
 }  // namespace
 
 int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
@@ -254,16 +533,29 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
                       cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_BWD, stream);
+  const bool packed = options().bwd_packed != 0;
   if (variant == kLight) {
-    render_bwd_kernel<kLight><<<grid, kTileThreads, 0, stream>>>(
-        img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas,
-        nullptr, img.n_contrib, nullptr, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar,
-        acc);
+    if (packed)
+      render_bwd2_kernel<kLight><<<grid, kBwd2Threads, 0, stream>>>(
+          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas,
+          nullptr, img.n_contrib, nullptr, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar,
+          acc);
+    else
+      render_bwd_kernel<kLight><<<grid, kTileThreads, 0, stream>>>(
+          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas,
+          nullptr, img.n_contrib, nullptr, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar,
+          acc);
   } else {
-    render_bwd_kernel<kFull><<<grid, kTileThreads, 0, stream>>>(
-        img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, nullptr,
-        img.final_T, img.n_contrib, img.first_contrib, cot.dL_dpix, cot.dL_ddepth, nullptr,
-        cot.dL_dvar, acc);
+    if (packed)
+      render_bwd2_kernel<kFull><<<grid, kBwd2Threads, 0, stream>>>(
+          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, nullptr,
+          img.final_T, img.n_contrib, img.first_contrib, cot.dL_dpix, cot.dL_ddepth, nullptr,
+          cot.dL_dvar, acc);
+    else
+      render_bwd_kernel<kFull><<<grid, kTileThreads, 0, stream>>>(
+          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, nullptr,
+          img.final_T, img.n_contrib, img.first_contrib, cot.dL_dpix, cot.dL_ddepth, nullptr,
+          cot.dL_dvar, acc);
   }
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;

@@ -321,6 +321,22 @@ def test_tile_local_binning_equals_radix_binning(built, variant):
         assert rel < 1e-4, (k, rel)
 
 
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_packed_and_scalar_backward_kernels_agree(built, variant):
+    sc, cam, scene = _scene(20000, 330, 250, sig=(1.0, 12.0), seed=45, backdrop=(variant == "full"))
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    _, g_a = pu.run_variant(mod, variant, cam, scene, cot)
+    old = pu.set_option("bwd_packed", 0)
+    try:
+        _, g_b = pu.run_variant(mod, variant, cam, scene, cot)
+    finally:
+        pu.set_option("bwd_packed", old)
+    for k in g_a:
+        rel, bad = pu.grad_mismatch(g_a[k], g_b[k], rtol=1e-3)
+        assert rel < 2e-4 and bad < 1e-3, (k, rel, bad)
+
+
 def test_very_long_tile_list_falls_back_to_radix(built):
     """More than 8192 entries in one tile: the frame takes the radix path and still matches the oracle."""
     sc = ge.load_scene_module()
