@@ -310,7 +310,7 @@ __device__ __forceinline__ unsigned block_mask4(const float4& r0, const float4& 
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(kBwd2Threads)
+__global__ void __launch_bounds__(kBwd2Threads, 8)
 render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                    const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
                    const float4* __restrict__ rec, const float* __restrict__ bg,
