@@ -160,6 +160,7 @@ class Frame:
         self.h2d_bytes = sum(t.numel() * 4 for t in [self.h_view, self.h_proj, self.h_campos, self.h_gt] + self.h_cots)
         self.d2h_bytes = 17 * 4
         self.last = None
+        self.copy_stream = None
 
     def _rasterizer(self, view, proj, campos):
         torch, cam, scene, dev = self.torch, self.cam, self.scene, self.device
@@ -194,16 +195,26 @@ class Frame:
         """Same frame with the per-frame inputs coming from pinned host memory and the result
         (loss, dL/dviewmatrix) going back to the host."""
         torch, dev = self.torch, self.device
+        main = torch.cuda.current_stream()
         view = self.h_view.to(dev, non_blocking=True).requires_grad_(True)
         proj = self.h_proj.to(dev, non_blocking=True)
         campos = self.h_campos.to(dev, non_blocking=True)
         gt = self.h_gt.to(dev, non_blocking=True)
-        cots = [c.to(dev, non_blocking=True) for c in self.h_cots]
+        # the cotangents are only needed by the backward: upload them on a copy stream while the
+        # forward runs (what an input pipeline does), and join before the backward
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream.wait_stream(main)
+        with torch.cuda.stream(self.copy_stream):
+            cots = [c.to(dev, non_blocking=True) for c in self.h_cots]
         rast = self._rasterizer(view.detach(), proj, campos)
         p = self.params
         res = rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"], shs=p["shs"],
                    scales=p["scales"], rotations=p["rotations"], viewmatrix=view, gt_depth=gt)
         outs = self._outs(res)
+        main.wait_stream(self.copy_stream)
+        for c in cots:
+            c.record_stream(main)
         torch.autograd.backward(outs, cots)
         with torch.no_grad():
             loss = sum((o * c).sum() for o, c in zip(outs, cots))

@@ -323,6 +323,74 @@ __device__ __forceinline__ uint2 pack_rect(uint2 rmin, uint2 rmax) {
   return make_uint2(rmin.x | (rmax.x << 16), rmin.y | (rmax.y << 16));
 }
 
+// Coalesced copy of `nrows` rows of m3 floats ([rows, m3] contiguous in global memory) into / out of
+// shared memory with row stride m3 + 1 (odd, so that the later one-row-per-thread accesses are bank
+// conflict free).  M3 > 0: compile-time row length (divisions become multiply-shifts, and for
+// M3 % 4 == 0 a 128-bit vector never straddles rows); M3 == 0: runtime row length.
+template <int M3>
+__device__ __forceinline__ void rows_to_smem(const float* __restrict__ src, float* smem, int nrows,
+                                             int m3_rt, int tid, int nthreads) {
+  const int m3 = M3 > 0 ? M3 : m3_rt;
+  const int row = m3 + 1;
+  const int nfloats = nrows * m3;
+  const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (nfloats >> 2) : 0;
+  const float4* src4 = reinterpret_cast<const float4*>(src);
+  for (int v = tid; v < nvec; v += nthreads) {
+    const float4 q = __ldg(src4 + v);
+    const int f = v << 2;
+    if (M3 > 0 && M3 % 4 == 0) {
+      const int g = f / m3;
+      float* d = smem + g * row + (f - g * m3);
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+    } else {
+      const float vals[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ff = f + k;
+        const int g = ff / m3;
+        smem[g * row + (ff - g * m3)] = vals[k];
+      }
+    }
+  }
+  for (int ff = (nvec << 2) + tid; ff < nfloats; ff += nthreads) {
+    const int g = ff / m3;
+    smem[g * row + (ff - g * m3)] = __ldg(src + ff);
+  }
+}
+
+template <int M3>
+__device__ __forceinline__ void smem_to_rows(float* __restrict__ dst, const float* smem, int nrows,
+                                             int m3_rt, int tid, int nthreads) {
+  const int m3 = M3 > 0 ? M3 : m3_rt;
+  const int row = m3 + 1;
+  const int nfloats = nrows * m3;
+  const int nvec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (nfloats >> 2) : 0;
+  float4* dst4 = reinterpret_cast<float4*>(dst);
+  for (int v = tid; v < nvec; v += nthreads) {
+    const int f = v << 2;
+    float4 q;
+    if (M3 > 0 && M3 % 4 == 0) {
+      const int g = f / m3;
+      const float* s = smem + g * row + (f - g * m3);
+      q = make_float4(s[0], s[1], s[2], s[3]);
+    } else {
+      float vals[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ff = f + k;
+        const int g = ff / m3;
+        vals[k] = smem[g * row + (ff - g * m3)];
+      }
+      q = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    }
+    dst4[v] = q;
+  }
+  for (int ff = (nvec << 2) + tid; ff < nfloats; ff += nthreads) {
+    const int g = ff / m3;
+    dst[ff] = smem[g * row + (ff - g * m3)];
+  }
+}
+
 // Spherical-harmonics constants (real SH basis up to degree 3, standard values).
 __device__ constexpr float kSH0 = 0.28209479177387814f;
 __device__ constexpr float kSH1 = 0.4886025119029199f;

@@ -37,7 +37,7 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
   return r;
 }
 
-template <int VARIANT>
+template <int VARIANT, int MT>  // MT: compile-time SH coefficient count (16/9/4/1) or 0 = runtime M
 __global__ void __launch_bounds__(kBwdThreads)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const int* __restrict__ radii, const float* __restrict__ shs,
@@ -59,24 +59,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const int nfloats = nvalid * M * 3;
 
   if (use_sh) {
-    const float* src = shs + (size_t)base * M * 3;
-    const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (nfloats >> 2) : 0;
-    const float4* src4 = reinterpret_cast<const float4*>(src);
-    for (int v = threadIdx.x; v < nvec; v += kBwdThreads) {
-      const float4 q = __ldg(src4 + v);
-      const int f = v << 2;
-      const float vals[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ff = f + k;
-        const int g = ff / (M * 3);
-        sh_smem[g * row + (ff - g * M * 3)] = vals[k];
-      }
-    }
-    for (int ff = (nvec << 2) + threadIdx.x; ff < nfloats; ff += kBwdThreads) {
-      const int g = ff / (M * 3);
-      sh_smem[g * row + (ff - g * M * 3)] = __ldg(src + ff);
-    }
+    rows_to_smem<MT * 3>(shs + (size_t)base * M * 3, sh_smem, nvalid, M * 3, threadIdx.x, kBwdThreads);
     __syncthreads();
   }
 
@@ -419,23 +402,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   // coalesced store of the block's dL/dSH slab
   if (use_sh && out.dL_dsh != nullptr) {
     __syncthreads();
-    float* dst = out.dL_dsh + (size_t)base * M * 3;
-    const int nvec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (nfloats >> 2) : 0;
-    float4* dst4 = reinterpret_cast<float4*>(dst);
-    for (int v = threadIdx.x; v < nvec; v += kBwdThreads) {
-      float vals[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ff = (v << 2) + k;
-        const int g = ff / (M * 3);
-        vals[k] = sh_smem[g * row + (ff - g * M * 3)];
-      }
-      dst4[v] = make_float4(vals[0], vals[1], vals[2], vals[3]);
-    }
-    for (int ff = (nvec << 2) + threadIdx.x; ff < nfloats; ff += kBwdThreads) {
-      const int g = ff / (M * 3);
-      dst[ff] = sh_smem[g * row + (ff - g * M * 3)];
-    }
+    smem_to_rows<MT * 3>(out.dL_dsh + (size_t)base * M * 3, sh_smem, nvalid, M * 3, threadIdx.x,
+                         kBwdThreads);
   }
 
   if (want_pose) {
@@ -514,17 +482,26 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
     GSR_CUDA_OK(cudaMemsetAsync(out.dL_dsh, 0, sizeof(float) * 3 * (size_t)P * (size_t)M, stream));
   }
   if (want_gauss || want_pose) {
+#define GSR_PRE_BWD(V, MT)                                                                       \
+  preprocess_bwd_kernel<V, MT><<<blocks, kBwdThreads, smem, stream>>>(                           \
+      P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
+      cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
+      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose)
+#define GSR_PRE_BWD_M(V)                                                                         \
+  switch (M) {                                                                                   \
+    case 16: GSR_PRE_BWD(V, 16); break;                                                          \
+    case 9: GSR_PRE_BWD(V, 9); break;                                                            \
+    case 4: GSR_PRE_BWD(V, 4); break;                                                            \
+    case 1: GSR_PRE_BWD(V, 1); break;                                                            \
+    default: GSR_PRE_BWD(V, 0); break;                                                           \
+  }
     if (variant == kLight) {
-      preprocess_bwd_kernel<kLight><<<blocks, kBwdThreads, smem, stream>>>(
-          P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D,
-          cam.view, cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx,
-          cam.tan_fovy, acc, g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose);
+      GSR_PRE_BWD_M(kLight)
     } else {
-      preprocess_bwd_kernel<kFull><<<blocks, kBwdThreads, smem, stream>>>(
-          P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D,
-          cam.view, cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx,
-          cam.tan_fovy, acc, g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose);
+      GSR_PRE_BWD_M(kFull)
     }
+#undef GSR_PRE_BWD_M
+#undef GSR_PRE_BWD
     GSR_LAUNCH_OK(debug, stream);
   }
   pose_finalize_kernel<<<1, 384, 0, stream>>>(blocks, pose_partials, out.dL_dview, want_pose);

@@ -163,6 +163,7 @@ constexpr int kMaxCoeffs = 16;
 // SH coefficients of a block of Gaussians are contiguous in memory ([P, M, 3] fp32): the block
 // streams its slab with coalesced 128-bit loads into shared memory (row stride M*3+1 floats to
 // spread banks) and each thread then reads its own row.
+template <int MT>  // compile-time number of SH coefficients (16 / 9 / 4 / 1) or 0 = runtime M
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ scales, float scale_modifier,
@@ -181,27 +182,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const int row = M * 3 + 1;
 
   if (shs != nullptr && colors_precomp == nullptr) {
-    const int nvalid = min(kPreThreads, P - base);
-    const int nfloats = nvalid * M * 3;
-    const float* src = shs + (size_t)base * M * 3;
-    // the slab start is 16-byte aligned whenever base*M*3*4 is (kPreThreads = 128 makes it so)
-    const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (nfloats >> 2) : 0;
-    const float4* src4 = reinterpret_cast<const float4*>(src);
-    for (int v = threadIdx.x; v < nvec; v += kPreThreads) {
-      const float4 q = __ldg(src4 + v);
-      const int f = v << 2;
-      const float vals[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ff = f + k;
-        const int g = ff / (M * 3);
-        sh_smem[g * row + (ff - g * M * 3)] = vals[k];
-      }
-    }
-    for (int ff = (nvec << 2) + threadIdx.x; ff < nfloats; ff += kPreThreads) {
-      const int g = ff / (M * 3);
-      sh_smem[g * row + (ff - g * M * 3)] = __ldg(src + ff);
-    }
+    rows_to_smem<MT * 3>(shs + (size_t)base * M * 3, sh_smem, min(kPreThreads, P - base), M * 3,
+                         threadIdx.x, kPreThreads);
     __syncthreads();
   }
   if (idx >= P) return;
@@ -332,11 +314,20 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
                           ? sizeof(float) * kPreThreads * (size_t)(M * 3 + 1) : 0;
   const int blocks = (P + kPreThreads - 1) / kPreThreads;
   StageScope st(ST_PRE_FWD, stream);
-  preprocess_fwd_kernel<<<blocks, kPreThreads, smem, stream>>>(
-      P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
-      colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,
-      cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,
-      g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0);
+#define GSR_PRE_FWD(MT)                                                                          \
+  preprocess_fwd_kernel<MT><<<blocks, kPreThreads, smem, stream>>>(                              \
+      P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,        \
+      colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,  \
+      cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,        \
+      g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0)
+  switch (M) {
+    case 16: GSR_PRE_FWD(16); break;
+    case 9: GSR_PRE_FWD(9); break;
+    case 4: GSR_PRE_FWD(4); break;
+    case 1: GSR_PRE_FWD(1); break;
+    default: GSR_PRE_FWD(0); break;
+  }
+#undef GSR_PRE_FWD
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
 }
