@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--variant", default="full", choices=["light", "full"])
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU oracle sample (0 = skip)")
     ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (gsr_set_option)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -352,6 +353,9 @@ def main():
     if a.impl == "b200":
         lib = ctypes.CDLL(ge.core_library_path())
         lib.gsr_stage_name.restype = ctypes.c_char_p
+        for kv in a.opt:
+            k, v = kv.split("=")
+            assert lib.gsr_set_option(k.encode(), int(v)) >= 0, "unknown option " + k
 
     def step():
         frame.zero_grad()

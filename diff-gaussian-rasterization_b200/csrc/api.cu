@@ -15,7 +15,7 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/1};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -380,7 +380,7 @@ int gsr_light_backward(
   const bool want_gauss = !map_off, want_pose = !track_off;
   if (want_gauss || want_pose) {
     BlendGrads cot{dL_dpix, dL_dpix_depth, dL_dpix_median_depth, dL_dpix_depth_var};
-    rc = launch_render_bwd(kLight, cam, g, b, img, background, gt_depth, alphas, cot, acc,
+    rc = launch_render_bwd(kLight, cam, g, b, img, background, gt_depth, alphas, cot, acc, P, R,
                            debug != 0, s);
     if (rc != GSR_OK) return rc;
   }
@@ -426,7 +426,7 @@ int gsr_full_backward(
     GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
   }
   BlendGrads cot{dL_dpix, dL_dpix_depth, nullptr, dL_dpix_uncertainty};
-  rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, false, s);
+  rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, s);
   if (rc != GSR_OK) return rc;
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
                    dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview};

@@ -128,7 +128,8 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
 // their tile's segment and every tile is sorted on chip by one CTA:
 //   (preprocess_fwd) one red per (Gaussian, tile) duplicate on a per-tile counter
 //   scan_tiles     one CTA: exclusive scan of the tile counters -> ranges, total, longest list
-//   scatter        slot = range.start + atomicAdd(fill[tile]);  entry = depth bits << 32 | index
+//   scatter        slot = atomicAdd(cursor[tile]) (cursor starts at the range start);
+//                  entry = depth bits << 32 | index
 //   sort_tiles     one CTA per tile: bitonic sort of the 64-bit entries in shared memory
 // The 64-bit entries are unique (index in the low word), so the result is the reference's order
 // (depth bits ascending, ties by ascending Gaussian index) regardless of the scatter order.
@@ -173,7 +174,7 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
     const uint32_t start = carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
     if (t < tiles) {
       ranges[t] = make_uint2(start, start + c);
-      tile_fill[t] = 0u;
+      tile_fill[t] = start;  // scatter cursor
     }
     __syncthreads();
     if (tid == 1023) s_carry = carry + s_warp[31];
@@ -186,25 +187,52 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
   if (tid == 0) { counters[0] = s_carry; counters[2] = s_max; }
 }
 
+// One thread per Gaussian.  tile_fill[t] starts at the tile's range start (scan_tiles_kernel), so
+// one atomic yields the slot.  A splat that covers many tiles is handed to the whole warp (lane i
+// takes tiles i, i+32, ...): a serial loop of dependent atomic -> store round trips in one thread
+// would otherwise set the kernel's duration.
 __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
                                        const uint32_t* __restrict__ tiles_touched,
                                        const uint2* __restrict__ rects, int grid_x,
-                                       const uint2* __restrict__ ranges,
                                        uint32_t* __restrict__ tile_fill,
                                        uint64_t* __restrict__ entries) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P) return;
-  if (tiles_touched[idx] == 0) return;
-  const uint2 rc = rects[idx];
-  const uint2 rmin = make_uint2(rc.x & 0xFFFFu, rc.y & 0xFFFFu);
-  const uint2 rmax = make_uint2(rc.x >> 16, rc.y >> 16);
-  const uint64_t entry = ((uint64_t)__float_as_uint(rec[3 * (size_t)idx + 1].w) << 32) | (uint32_t)idx;
-  for (uint32_t y = rmin.y; y < rmax.y; ++y)
-    for (uint32_t x = rmin.x; x < rmax.x; ++x) {
-      const uint32_t t = y * (uint32_t)grid_x + x;
-      const uint32_t slot = ranges[t].x + atomicAdd(tile_fill + t, 1u);
-      entries[slot] = entry;
+  const int lane = threadIdx.x & 31;
+  uint32_t n = (idx < P) ? tiles_touched[idx] : 0u;
+  uint2 rc = make_uint2(0u, 0u);
+  uint64_t entry = 0ull;
+  if (n != 0u) {
+    rc = rects[idx];
+    entry = ((uint64_t)__float_as_uint(rec[3 * (size_t)idx + 1].w) << 32) | (uint32_t)idx;
+  }
+  constexpr uint32_t kWide = 8;  // splats with more tiles than this are processed by the whole warp
+  unsigned wide = __ballot_sync(0xffffffffu, n > kWide);
+  while (wide) {
+    const int src = __ffs(wide) - 1;
+    wide &= wide - 1;
+    const uint32_t rx = __shfl_sync(0xffffffffu, rc.x, src), ry = __shfl_sync(0xffffffffu, rc.y, src);
+    const uint32_t e_lo = __shfl_sync(0xffffffffu, (uint32_t)entry, src);
+    const uint32_t e_hi = __shfl_sync(0xffffffffu, (uint32_t)(entry >> 32), src);
+    const uint32_t x0 = rx & 0xFFFFu, x1 = rx >> 16, y0 = ry & 0xFFFFu, y1 = ry >> 16;
+    const uint32_t w = x1 - x0, total = w * (y1 - y0);
+    const uint64_t e = ((uint64_t)e_hi << 32) | e_lo;
+    for (uint32_t q = lane; q < total; q += 32) {
+      const uint32_t t = (y0 + q / w) * (uint32_t)grid_x + x0 + q % w;
+      entries[atomicAdd(tile_fill + t, 1u)] = e;
     }
+  }
+  if (n != 0u && n <= kWide) {
+    const uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu, y1 = rc.y >> 16;
+    const uint32_t w = x1 - x0;
+    (void)y1;
+    uint32_t slots[kWide];
+#pragma unroll
+    for (uint32_t u = 0; u < kWide; ++u)  // issue all atomics first, then the dependent stores
+      if (u < n) slots[u] = atomicAdd(tile_fill + (y0 + u / w) * (uint32_t)grid_x + x0 + u % w, 1u);
+#pragma unroll
+    for (uint32_t u = 0; u < kWide; ++u)
+      if (u < n) entries[slots[u]] = entry;
+  }
 }
 
 // Bitonic sort of one tile's entries with E elements per thread held in registers (element index
@@ -378,7 +406,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     {
       StageScope st(ST_EMIT, stream);
       scatter_entries_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
-          P, g.rec, g.tiles_touched, g.rect, cam.grid_x, img.ranges, img.tile_fill, b.keys_unsorted);
+          P, g.rec, g.tiles_touched, g.rect, cam.grid_x, img.tile_fill, b.keys_unsorted);
       GSR_LAUNCH_OK(debug, stream);
     }
     {

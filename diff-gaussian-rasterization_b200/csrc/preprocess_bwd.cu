@@ -483,6 +483,8 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   }
   if (want_gauss || want_pose) {
 #define GSR_PRE_BWD(V, MT)                                                                       \
+  cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                       cudaSharedmemCarveoutMaxShared);                                          \
   preprocess_bwd_kernel<V, MT><<<blocks, kBwdThreads, smem, stream>>>(                           \
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \

@@ -315,6 +315,8 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
   const int blocks = (P + kPreThreads - 1) / kPreThreads;
   StageScope st(ST_PRE_FWD, stream);
 #define GSR_PRE_FWD(MT)                                                                          \
+  cudaFuncSetAttribute(preprocess_fwd_kernel<MT>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                       cudaSharedmemCarveoutMaxShared);                                          \
   preprocess_fwd_kernel<MT><<<blocks, kPreThreads, smem, stream>>>(                              \
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,        \
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,  \

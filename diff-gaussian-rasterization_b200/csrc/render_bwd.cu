@@ -529,11 +529,15 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
 
 int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
                       const ImgState& img, const float* bg, const float* gt_depth,
-                      const float* alphas, const BlendGrads& cot, float* acc, bool debug,
-                      cudaStream_t stream) {
+                      const float* alphas, const BlendGrads& cot, float* acc, int num_gaussians,
+                      int num_entries, bool debug, cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_BWD, stream);
-  const bool packed = options().bwd_packed != 0;
+  // auto (2): the packed kernel works on 8x8 pixel blocks and wins when splats are large enough to
+  // fill them (measured: C3, 1.97 duplicates per Gaussian: 0.87 vs 0.96 ms); small splats (C4, 1.30
+  // duplicates per Gaussian: 2.00 vs 1.88 ms) are better served by the 8x4-block kernel.
+  const int mode = options().bwd_packed;
+  const bool packed = mode == 1 || (mode == 2 && (double)num_entries >= 1.6 * (double)num_gaussians);
   if (variant == kLight) {
     if (packed)
       render_bwd2_kernel<kLight><<<grid, kBwd2Threads, 0, stream>>>(

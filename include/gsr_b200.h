@@ -81,8 +81,9 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   segment and each tile is sorted on chip (same order as the reference's
  *                   device-wide (tile | depth) radix sort; tiles with more than 8192 entries make
  *                   the frame fall back to the radix path); 0: always the radix path.
- *   "bwd_packed"    1 (default): backward blend kernel with two pixels per lane and packed fp32x2
- *                   arithmetic; 0: the one-pixel-per-lane kernel (same results up to summation order).
+ *   "bwd_packed"    backward blend kernel: 1 = two pixels per lane, packed fp32x2 arithmetic, 8x8
+ *                   pixel blocks; 0 = one pixel per lane, 8x4 blocks; 2 (default) = pick per call
+ *                   from the number of duplicates per Gaussian (same results up to summation order).
  * Returns the previous value, or GSR_E_INVALID for an unknown key. */
 GSR_API int gsr_set_option(const char* key, int value);
 GSR_API int gsr_get_option(const char* key);

@@ -326,9 +326,10 @@ def test_packed_and_scalar_backward_kernels_agree(built, variant):
     sc, cam, scene = _scene(20000, 330, 250, sig=(1.0, 12.0), seed=45, backdrop=(variant == "full"))
     cot = sc.make_cotangents(cam, _n_aux(variant))
     mod = built.load_variant(variant)
-    _, g_a = pu.run_variant(mod, variant, cam, scene, cot)
-    old = pu.set_option("bwd_packed", 0)
+    old = pu.set_option("bwd_packed", 1)
     try:
+        _, g_a = pu.run_variant(mod, variant, cam, scene, cot)
+        pu.set_option("bwd_packed", 0)
         _, g_b = pu.run_variant(mod, variant, cam, scene, cot)
     finally:
         pu.set_option("bwd_packed", old)
