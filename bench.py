@@ -389,6 +389,14 @@ def main():
             r = mod._C.rasterize_gaussians(*args)
             num_rendered, num_related = int(r[0]), int(r[1])
         del r
+        if os.environ.get("GSR_BENCH_DEBUG"):
+            import hashlib
+            hh = hashlib.sha1()
+            for t in args:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    hh.update(t.detach().cpu().numpy().tobytes())
+            ns = [int(mod._C.rasterize_gaussians(*args)[0]) for _ in range(5)]
+            log("debug: device input sha1 %s  N over 5 probes %s" % (hh.hexdigest()[:16], ns))
     except Exception as e:  # informational only
         log("count probe failed: %r" % (e,))
 

@@ -124,9 +124,15 @@ def make_scene(P, cam: Camera, sigma_px=(1.0, 8.0), seed=0, backdrop=False,
     p_cam = torch.stack([x, y, z], dim=1)
     R = cam.w2c[:3, :3]
     t = cam.w2c[:3, 3]
-    means = (p_cam - t) @ R  # R^T (p - t), row-vector form
+    # R^T (p - t), row-vector form.  Written with elementwise ops only (no GEMM, no library
+    # reduction): a threaded BLAS may pick a different summation order from run to run, and a 1-ulp
+    # difference in one mean is enough to move a splat across a tile boundary (num_rendered +-1).
+    dlt = (p_cam - t).double()
+    Rd = R.double()
+    means = (dlt[:, 0:1] * Rd[0] + dlt[:, 1:2] * Rd[1] + dlt[:, 2:3] * Rd[2]).float()
     q = torch.randn(P, 4, generator=g, dtype=torch.float32)
-    q = q / q.norm(dim=1, keepdim=True)
+    qd = q.double()
+    q = (qd / torch.sqrt(qd[:, 0:1] ** 2 + qd[:, 1:2] ** 2 + qd[:, 2:3] ** 2 + qd[:, 3:4] ** 2)).float()
     shs = torch.empty(P, 16, 3, dtype=torch.float32)
     shs[:, 0, :] = 3.0 * U(P, 3) - 1.5
     shs[:, 1:, :] = 0.1 * torch.randn(P, 15, 3, generator=g, dtype=torch.float32)
