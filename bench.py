@@ -293,6 +293,8 @@ def main():
     ap.add_argument("--variant", default="full", choices=["light", "full"])
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU oracle sample (0 = skip)")
     ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--dp-mode", default="factorized_sh", choices=["allreduce", "factorized_sh"],
+                    help="gradient exchange at N > 1 (diff-gaussian-rasterization_b200/dp.py)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (gsr_set_option)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -345,9 +347,11 @@ def main():
     reducer = None
     if world > 1:
         dp = ge.load_dp_module()
-        reducer = dp.SceneGradReducer({k: tuple(v.shape) for k, v in frame.params.items()}, device)
+        shapes = {k: tuple(v.shape) for k, v in frame.params.items()}
+        dp_mode = a.dp_mode if a.impl == "b200" else "allreduce"   # the reference has no masked colour output
+        reducer = dp.SceneGradReducer(shapes, device, mode=dp_mode, means3D=frame.params["means3D"], sh_degree=3)
         zero_copy = reducer.attach(mod)   # B200 arm: backward writes into the flat buffer directly
-        log("rank %d: gradient arena attached: %s" % (rank, zero_copy))
+        log("rank %d: exchange mode %s, gradient arena attached: %s" % (rank, dp_mode, zero_copy))
 
     lib = None
     if a.impl == "b200":
@@ -446,8 +450,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "variant": a.variant, "gaussians": P, "width": W, "height": H,
                    "num_rendered": num_rendered, "num_related": num_related,
-                   "parallelism": "view-dp%d (one view per GPU, one all-reduce of %d MB of scene gradients)" % (
-                       world, (reducer.bytes_per_step() >> 20) if reducer else 0) if world > 1 else "single GPU",
+                   "parallelism": ("view-dp%d (one view per GPU; exchange '%s': %d MB of scene gradients per rank "
+                                   "and step)" % (world, reducer.mode, reducer.bytes_per_step() >> 20))
+                   if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: %d MB of scene parameters + %d MB of per-frame state are "
                          "streamed every step (126 MB L2)" % ((59 * 4 * P) >> 20, (48 * P + 40 * (num_rendered or 0)) >> 20)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frame.h2d_bytes,

@@ -9,5 +9,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
   m.def("mark_visible", &markVisible);
   // extension (not in the reference): flat scene-gradient arena for view-level data parallelism
-  m.def("set_grad_arena", &setGradArena);
+  m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false);
+  m.def("sh_grad_from_views", &shGradFromViews);
 }

@@ -35,6 +35,9 @@ torch::Tensor prep(const torch::Tensor& t, const torch::Device& dev, const char*
 const float* fptr(const torch::Tensor& t) {
   return t.defined() ? t.data_ptr<float>() : nullptr;
 }
+float* fptr_mut(const torch::Tensor& t) {
+  return t.defined() ? t.data_ptr<float>() : nullptr;
+}
 
 void check_rc(int rc, const char* who) {
   TORCH_CHECK(rc == GSR_OK, who, " failed (", rc, "): ", gsr_last_error());
@@ -45,16 +48,38 @@ torch::Tensor scratch_for(int P, const torch::TensorOptions& fopts) {
 }
 
 torch::Tensor g_grad_arena;  // see setGradArena
+bool g_arena_factorized = false;
 
 struct SceneGrads {
   torch::Tensor means3D, sh, opacity, scales, rotations;
+  torch::Tensor masked_color;  // factorized arena only
+  bool factorized = false;
 };
 
 // the five scene-parameter gradients: views of the registered arena when it fits, fresh tensors otherwise
 SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torch::TensorOptions& fopts) {
   SceneGrads g;
+  const bool arena_ok = g_grad_arena.defined() && g_grad_arena.device() == like.device() &&
+                        g_grad_arena.scalar_type() == torch::kFloat32 && g_grad_arena.is_contiguous() &&
+                        P > 0 && P % 4 == 0;
+  if (arena_ok && g_arena_factorized && M > 0 && g_grad_arena.numel() == (int64_t)P * 14 + 4) {
+    int64_t off = 0;
+    auto take = [&](int64_t n, std::vector<int64_t> shape) {
+      torch::Tensor t = g_grad_arena.narrow(0, off, n).view(shape);
+      off += n;
+      return t;
+    };
+    g.factorized = true;
+    g.masked_color = take((int64_t)P * 3, {P, 3});
+    off += 4;  // campos + pad, filled by the caller
+    g.means3D = take((int64_t)P * 3, {P, 3});
+    g.opacity = take((int64_t)P, {P, 1});
+    g.scales = take((int64_t)P * 3, {P, 3});
+    g.rotations = take((int64_t)P * 4, {P, 4});
+    return g;  // g.sh stays undefined: dL_dsh is not written in this mode
+  }
   const int64_t need = (int64_t)P * (3 + 3 * (int64_t)M + 1 + 3 + 4);
-  if (g_grad_arena.defined() && g_grad_arena.numel() == need && g_grad_arena.device() == like.device() &&
+  if (!g_arena_factorized && g_grad_arena.defined() && g_grad_arena.numel() == need && g_grad_arena.device() == like.device() &&
       g_grad_arena.scalar_type() == torch::kFloat32 && g_grad_arena.is_contiguous() && P > 0 &&
       P % 4 == 0 /* keeps every slice 16-byte aligned for the kernels' 128-bit stores */) {
     int64_t off = 0;
@@ -175,7 +200,13 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dconic = torch::empty({P, 2, 2}, fopts);
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
-  torch::Tensor dL_dsh = sg.sh;
+  torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
+  gsr_backward_extras extras{nullptr, 0};
+  if (sg.factorized) {
+    extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
+    extras.skip_sh_grad = 1;
+    g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
+  }
   torch::Tensor dL_dscales = sg.scales;
   torch::Tensor dL_drotations = sg.rotations;
   torch::Tensor dL_dview = torch::empty({1, 4, 4}, fopts);
@@ -201,10 +232,10 @@ RasterizeGaussiansBackwardCUDA(
       reinterpret_cast<char*>(bb.data_ptr()), reinterpret_cast<char*>(ib.data_ptr()), fptr(gc),
       fptr(gd), fptr(gm), fptr(gv), dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(),
       dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), dL_ddepths.data_ptr<float>(),
-      dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), dL_dsh.data_ptr<float>(),
+      dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), fptr_mut(dL_dsh),
       dL_dscales.data_ptr<float>(), dL_drotations.data_ptr<float>(), debug ? 1 : 0, fptr(per),
       dL_dview.data_ptr<float>(), fptr(gtd), track_off ? 1 : 0, map_off ? 1 : 0,
-      scratch.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream());
+      scratch.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream(), &extras);
   check_rc(rc, "gsr_light_backward");
   return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh,
                          dL_dscales, dL_drotations, dL_dview);
@@ -295,7 +326,13 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dconic = torch::empty({P, 2, 2}, fopts);
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
-  torch::Tensor dL_dsh = sg.sh;
+  torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
+  gsr_backward_extras extras{nullptr, 0};
+  if (sg.factorized) {
+    extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
+    extras.skip_sh_grad = 1;
+    g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
+  }
   torch::Tensor dL_dscales = sg.scales;
   torch::Tensor dL_drotations = sg.rotations;
   torch::Tensor dL_dview = torch::empty({4, 4}, fopts);
@@ -320,10 +357,10 @@ RasterizeGaussiansBackwardCUDA(
       reinterpret_cast<char*>(bb.data_ptr()), reinterpret_cast<char*>(ib.data_ptr()), fptr(gc),
       fptr(gd), fptr(gu), dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(),
       dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), dL_dgau_depths.data_ptr<float>(),
-      dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), dL_dsh.data_ptr<float>(),
+      dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), fptr_mut(dL_dsh),
       dL_dscales.data_ptr<float>(), dL_drotations.data_ptr<float>(), fptr(per),
       dL_dview.data_ptr<float>(), fptr(gtd), scratch.data_ptr<float>(),
-      at::cuda::getCurrentCUDAStream().stream());
+      at::cuda::getCurrentCUDAStream().stream(), &extras);
   check_rc(rc, "gsr_full_backward");
   return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh,
                          dL_dscales, dL_drotations, dL_dview);
@@ -331,15 +368,33 @@ RasterizeGaussiansBackwardCUDA(
 
 #endif
 
-void setGradArena(const torch::Tensor& arena) {
+void setGradArena(const torch::Tensor& arena, bool factorized_sh) {
+  g_arena_factorized = factorized_sh;
   if (!arena.defined() || arena.numel() == 0) {
     g_grad_arena = torch::Tensor();
+    g_arena_factorized = false;
     return;
   }
   TORCH_CHECK(arena.is_cuda() && arena.scalar_type() == torch::kFloat32 && arena.is_contiguous() &&
                   arena.dim() == 1,
               "grad arena must be a contiguous 1-D float32 CUDA tensor");
   g_grad_arena = arena;
+}
+
+torch::Tensor shGradFromViews(const torch::Tensor& means3D, const torch::Tensor& gathered, const int degree,
+                              const int M) {
+  TORCH_CHECK(means3D.is_cuda() && gathered.is_cuda(), "sh_grad_from_views needs CUDA tensors");
+  const c10::cuda::CUDAGuard guard(means3D.device());
+  const auto dev = means3D.device();
+  const int P = means3D.size(0);
+  const auto mu = prep(means3D, dev, "means3D"), ga = prep(gathered, dev, "gathered");
+  TORCH_CHECK(ga.dim() == 2 && ga.size(1) == (int64_t)P * 3 + 4, "gathered must be [nviews, 3P + 4]");
+  torch::Tensor out = torch::empty({P, M, 3}, means3D.options().dtype(torch::kFloat32));
+  const int rc = gsr_sh_grad_from_views(P, degree, M, fptr(mu), (int)ga.size(0), fptr(ga), (size_t)ga.size(1),
+                                        fptr(ga) + (size_t)P * 3, (size_t)ga.size(1), out.data_ptr<float>(),
+                                        at::cuda::getCurrentCUDAStream().stream());
+  check_rc(rc, "gsr_sh_grad_from_views");
+  return out;
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,

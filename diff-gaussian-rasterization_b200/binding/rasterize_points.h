@@ -73,7 +73,18 @@ RasterizeGaussiansBackwardCUDA(
 // registered and its size matches, RasterizeGaussiansBackwardCUDA writes those five gradients
 // straight into it (the returned tensors are views), so a data-parallel caller can all-reduce one
 // buffer without packing.  Not part of the reference surface.
-void setGradArena(const torch::Tensor& arena);
+//
+// factorized_sh = true selects the layout used by the SH-factorized exchange
+//   [ dL_dcolor_masked (3P) | campos (3) + pad (1) | means3D (3P) | opacity (P) | scales (3P) | rotations (4P) ]
+// (14P + 4 floats): the backward then writes the masked colour gradient and the camera position
+// instead of dL_dsh (whose returned tensor is undefined / None); the summed dL_dsh of all views is
+// rebuilt with shGradFromViews after an all-gather of the first 3P + 4 floats.
+void setGradArena(const torch::Tensor& arena, bool factorized_sh);
+
+// gathered: [nviews, 3P + 4] (rows = the first 3P + 4 floats of each rank's factorized arena).
+// Returns sum over views of dL_dsh, [P, M, 3].
+torch::Tensor shGradFromViews(const torch::Tensor& means3D, const torch::Tensor& gathered, const int degree,
+                              const int M);
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,
                           torch::Tensor& projmatrix);

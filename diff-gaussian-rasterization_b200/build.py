@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 BIND = os.path.join(HERE, "binding")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
-CORE_SOURCES = ["api.cu", "preprocess_fwd.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu",
+CORE_SOURCES = ["api.cu", "preprocess_fwd.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "sh_grad_views.cu",
                 "preprocess_bwd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")

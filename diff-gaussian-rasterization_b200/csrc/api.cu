@@ -352,7 +352,7 @@ int gsr_light_backward(
     float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
     float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug,
     const float* perspec_matrix, float* dL_dview, const float* gt_depth, int track_off,
-    int map_off, float* scratch, void* stream) {
+    int map_off, float* scratch, void* stream, const gsr_backward_extras* extras) {
   g_err[0] = 0;
   (void)colors_precomp;  // colours come from the packed record written by the forward
   cudaStream_t s = (cudaStream_t)stream;
@@ -385,7 +385,11 @@ int gsr_light_backward(
     if (rc != GSR_OK) return rc;
   }
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
-                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview};
+                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr};
+  if (extras != nullptr) {
+    out.dL_dcolor_masked = extras->dL_dcolor_masked;
+    if (extras->skip_sh_grad) out.dL_dsh = nullptr;
+  }
   return launch_preprocess_bwd(kLight, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
                                out, want_gauss, want_pose, debug != 0, s);
@@ -401,7 +405,7 @@ int gsr_full_backward(
     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth,
     float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
     const float* perspec_matrix, float* dL_dview, const float* gt_depth, float* scratch,
-    void* stream) {
+    void* stream, const gsr_backward_extras* extras) {
   g_err[0] = 0;
   (void)colors_precomp;
   cudaStream_t s = (cudaStream_t)stream;
@@ -429,7 +433,11 @@ int gsr_full_backward(
   rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, s);
   if (rc != GSR_OK) return rc;
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
-                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview};
+                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr};
+  if (extras != nullptr) {
+    out.dL_dcolor_masked = extras->dL_dcolor_masked;
+    if (extras->skip_sh_grad) out.dL_dsh = nullptr;
+  }
   return launch_preprocess_bwd(kFull, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
                                out, true, true, false, s);

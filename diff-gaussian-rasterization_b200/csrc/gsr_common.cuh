@@ -450,6 +450,7 @@ struct GaussGradOut {
   float* dL_dmean2D; float* dL_dconic; float* dL_dopacity; float* dL_dcolor; float* dL_ddepth;
   float* dL_dmean3D; float* dL_dcov3D; float* dL_dsh; float* dL_dscale; float* dL_drot;
   float* dL_dview;
+  float* dL_dcolor_masked;  // optional [P,3]: dL/dcolor with clamped channels zeroed (see gsr_backward_extras)
 };
 
 int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D,

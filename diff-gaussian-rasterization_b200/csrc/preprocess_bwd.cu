@@ -77,6 +77,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     }
     if (out.dL_dopacity) out.dL_dopacity[idx] = 0.f;
     st3(out.dL_dcolor, idx, 0.f, 0.f, 0.f);
+    st3(out.dL_dcolor_masked, idx, 0.f, 0.f, 0.f);
     if (out.dL_ddepth) out.dL_ddepth[idx] = 0.f;
     st3(out.dL_dmean3D, idx, 0.f, 0.f, 0.f);
     if (out.dL_dcov3D) {
@@ -224,6 +225,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         const unsigned char cb = clamped[idx];
         const float dR[3] = {g_r * ((cb & 1) ? 0.f : 1.f), g_g * ((cb & 2) ? 0.f : 1.f),
                              g_b * ((cb & 4) ? 0.f : 1.f)};
+        st3(out.dL_dcolor_masked, idx, dR[0], dR[1], dR[2]);
         float dx_[3] = {0.f, 0.f, 0.f}, dy_[3] = {0.f, 0.f, 0.f}, dz_[3] = {0.f, 0.f, 0.f};
         float coef[16];
 #pragma unroll
@@ -425,27 +427,31 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   }
 }
 
-// Adds the per-block pose partials in a fixed order and scatters the 12 live entries into the
-// 16-float column-major dL/dviewmatrix (entries 3,7,11,15 stay 0, as in the reference).
-__global__ void __launch_bounds__(384)
+// Adds the per-block pose partials in a fixed order (deterministic, no atomics) and scatters the
+// 12 live entries into the 16-float column-major dL/dviewmatrix (entries 3,7,11,15 are 0, as in
+// the reference).  One CTA per live entry: 1024 threads stride over the blocks, then a tree.
+__global__ void __launch_bounds__(1024)
 pose_finalize_kernel(int nblocks, const float* __restrict__ partials, float* __restrict__ dL_dview,
                      bool want_pose) {
-  __shared__ float s[32][12];
-  const int k = threadIdx.x % 12;
-  const int lane = threadIdx.x / 12;  // 32 strided accumulators per entry
+  __shared__ float s[32];
+  const int k = blockIdx.x;  // pose[] order: (v0,v1,v2),(v4,v5,v6),(v8,v9,v10),(v12,v13,v14)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float sum = 0.f;
   if (want_pose)
-    for (int b = lane; b < nblocks; b += 32) sum += partials[(size_t)b * 12 + k];
-  s[lane][k] = sum;
+    for (int b = tid; b < nblocks; b += 1024) sum += partials[(size_t)b * 12 + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s[warp] = sum;
   __syncthreads();
-  if (threadIdx.x < 16) {
-    float total = 0.f;
-    const int col = threadIdx.x >> 2, rowi = threadIdx.x & 3;  // flat index = 4*col + row
-    if (rowi < 3) {
-      const int kk = 3 * col + rowi;  // pose[] order: (v0,v1,v2),(v4,v5,v6),(v8,v9,v10),(v12,v13,v14)
-      for (int l = 0; l < 32; ++l) total += s[l][kk];
+  if (warp == 0) {
+    float t = s[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+      const int col = k / 3, rowi = k % 3;
+      dL_dview[4 * col + rowi] = t;
+      if (rowi == 0) dL_dview[4 * col + 3] = 0.f;
     }
-    dL_dview[threadIdx.x] = total;
   }
 }
 
@@ -472,6 +478,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
     GSR_CUDA_OK(zero(out.dL_dconic, 4 * (size_t)P));
     GSR_CUDA_OK(zero(out.dL_dopacity, (size_t)P));
     GSR_CUDA_OK(zero(out.dL_dcolor, 3 * (size_t)P));
+    GSR_CUDA_OK(zero(out.dL_dcolor_masked, 3 * (size_t)P));
     GSR_CUDA_OK(zero(out.dL_ddepth, (size_t)P));
     GSR_CUDA_OK(zero(out.dL_dmean3D, 3 * (size_t)P));
     GSR_CUDA_OK(zero(out.dL_dcov3D, 6 * (size_t)P));
@@ -506,7 +513,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
 #undef GSR_PRE_BWD
     GSR_LAUNCH_OK(debug, stream);
   }
-  pose_finalize_kernel<<<1, 384, 0, stream>>>(blocks, pose_partials, out.dL_dview, want_pose);
+  pose_finalize_kernel<<<12, 1024, 0, stream>>>(blocks, pose_partials, out.dL_dview, want_pose);
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
 }

@@ -1,17 +1,23 @@
 """View-level data parallelism for the rasterizer (new work: the reference has no multi-GPU code).
 
 One process per GPU; every rank holds the same replicated scene parameters and renders its own
-camera view(s) forward+backward.  The only exchange step is ONE all-reduce (sum) of the
-scene-parameter gradients, packed into a single flat fp32 buffer
+camera view(s) forward+backward.  The only exchange step is the sum over ranks of the
+scene-parameter gradients; per-view results (images, radii, dL/dviewmatrix, dL/dmeans2D) are NOT
+reduced.  Two exchange modes:
 
-    [ dL/dmeans3D (3P) | dL/dsh (3MP) | dL/dopacity (P) | dL/dscales (3P) | dL/drotations (4P) ]
+  "allreduce"  (default)  ONE all-reduce (sum) of a single flat fp32 buffer
+        [ dL/dmeans3D (3P) | dL/dsh (3MP) | dL/dopacity (P) | dL/dscales (3P) | dL/drotations (4P) ]
+      = 59 floats = 236 bytes per Gaussian at M = 16.
+  "factorized_sh"  dL/dsh of a view is the rank-1 product basis_k(view direction) x masked dL/dcolor,
+      so ranks all-gather 3 floats per Gaussian (+ the camera position) and all-reduce only the other
+      11 floats; every rank rebuilds the summed dL/dsh locally (`_C.sh_grad_from_views`).  Same result
+      up to summation order, 14 instead of 59 floats per Gaussian on the wire.
 
-= 59 floats = 236 bytes per Gaussian at M = 16.  Per-view results (images, radii,
-dL/dviewmatrix, dL/dmeans2D) are NOT reduced.  The all-reduce runs on a side stream so that the
-caller can overlap it with the next view's forward; `wait()` makes the reduced gradients visible
-to the current stream.
-
-Works with any torch.distributed backend: NCCL over NVLink on the B200 box, gloo on CPU (tests).
+With `attach()` the backward of the B200-native packages writes its gradients straight into the
+flat buffer (no packing copy).  The collectives run on a side stream; `wait()` makes the reduced
+gradients visible to the current stream.  Works with any torch.distributed backend: NCCL over NVLink
+on the B200 box, gloo on CPU (tests; the CPU path of the SH rebuild below is a plain-torch
+restatement used by those tests only).
 """
 from collections import OrderedDict
 
@@ -19,6 +25,13 @@ import torch
 import torch.distributed as dist
 
 PARAM_ORDER = ("means3D", "shs", "opacities", "scales", "rotations")
+FACT_ORDER = ("means3D", "opacities", "scales", "rotations")  # all-reduced part of the factorized layout
+
+SH_C0 = 0.28209479177387814
+SH_C1 = 0.4886025119029199
+SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154,
+         -0.4570457994644658, 1.445305721320277, -0.5900435899266435)
 
 
 def shard_views(num_views, rank, world_size):
@@ -26,53 +39,102 @@ def shard_views(num_views, rank, world_size):
     return list(range(rank, num_views, world_size))
 
 
+def sh_basis(dirs, degree):
+    """Real SH basis values [P, (degree+1)^2] for unit directions [P,3] (forward.cu:20-71)."""
+    x, y, z = dirs[:, 0], dirs[:, 1], dirs[:, 2]
+    b = [torch.full_like(x, SH_C0)]
+    if degree > 0:
+        b += [-SH_C1 * y, SH_C1 * z, -SH_C1 * x]
+    if degree > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        b += [SH_C2[0] * xy, SH_C2[1] * yz, SH_C2[2] * (2 * zz - xx - yy), SH_C2[3] * xz, SH_C2[4] * (xx - yy)]
+    if degree > 2:
+        b += [SH_C3[0] * y * (3 * xx - yy), SH_C3[1] * xy * z, SH_C3[2] * y * (4 * zz - xx - yy),
+              SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy), SH_C3[4] * x * (4 * zz - xx - yy),
+              SH_C3[5] * z * (xx - yy), SH_C3[6] * x * (xx - 3 * yy)]
+    return torch.stack(b, dim=1)
+
+
+def sh_grad_from_views_torch(means3D, gathered, degree, M):
+    """Plain-torch restatement of gsr_sh_grad_from_views (CPU tests only)."""
+    P = means3D.shape[0]
+    out = torch.zeros(P, M, 3, dtype=torch.float32, device=means3D.device)
+    nc = (degree + 1) ** 2
+    for v in range(gathered.shape[0]):
+        dR = gathered[v, :3 * P].view(P, 3)
+        campos = gathered[v, 3 * P:3 * P + 3]
+        d = means3D - campos
+        d = d / d.norm(dim=1, keepdim=True)
+        out[:, :nc, :] += sh_basis(d, degree)[:, :, None] * dR[:, None, :]
+    return out
+
+
 class SceneGradReducer:
-    def __init__(self, shapes, device, group=None, average=False):
-        """shapes: mapping name -> shape for the entries of PARAM_ORDER that exist."""
-        self.group = group
-        self.average = average
-        self.slices = OrderedDict()
-        off = 0
-        for name in PARAM_ORDER:
-            if name in shapes and shapes[name] is not None:
-                n = 1
-                for s in shapes[name]:
-                    n *= int(s)
-                self.slices[name] = (off, n, tuple(int(s) for s in shapes[name]))
-                off += n
-        self.numel = off
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+    def __init__(self, shapes, device, group=None, average=False, mode="allreduce", means3D=None,
+                 sh_degree=3):
+        """shapes: mapping name -> shape for the entries of PARAM_ORDER that exist.
+        mode "factorized_sh" additionally needs the (replicated) means3D parameter tensor."""
+        assert mode in ("allreduce", "factorized_sh")
+        self.group, self.average, self.mode = group, average, mode
         self.is_cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
-        self._work = None
-        self._done = None
+        self._work, self._done, self._attached = None, None, None
+        self.slices = OrderedDict()
+        num = lambda shape: int(torch.Size(shape).numel())
+        if mode == "allreduce":
+            off = 0
+            for name in PARAM_ORDER:
+                if shapes.get(name) is not None:
+                    self.slices[name] = (off, num(shapes[name]), tuple(int(s) for s in shapes[name]))
+                    off += num(shapes[name])
+            self.numel = off
+        else:
+            assert means3D is not None and shapes.get("shs") is not None
+            self.means3D, self.sh_degree = means3D, int(sh_degree)
+            self.P = P = int(shapes["means3D"][0])
+            self.M = int(shapes["shs"][1])
+            self.head = 3 * P + 4           # masked colour gradient + camera position (+ pad): all-gathered
+            off = self.head
+            for name in FACT_ORDER:
+                self.slices[name] = (off, num(shapes[name]), tuple(int(s) for s in shapes[name]))
+                off += num(shapes[name])
+            self.numel = off                # 14 P + 4
+            self.sh_shape = tuple(int(s) for s in shapes["shs"])
+            self.sh_sum = None
+            self.gathered = None
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
 
-    def views(self):
-        """Per-parameter views into the flat buffer (valid after wait())."""
-        return {k: self.flat[o:o + n].view(shape) for k, (o, n, shape) in self.slices.items()}
-
-    def pack(self, grads):
-        for k, (o, n, _shape) in self.slices.items():
-            g = grads[k]
-            self.flat[o:o + n].copy_(g.reshape(-1) if g is not None else 0)
-
+    # ---- wiring -------------------------------------------------------------------------------
     def attach(self, rasterizer_module):
         """Register the flat buffer as the gradient arena of a B200-native rasterizer package
-        (`_C.set_grad_arena`): its backward then writes the five scene gradients straight into
-        the buffer and reduce_async() needs no packing copy.  Returns False (and changes nothing)
-        for packages without that extension, e.g. the reference build."""
+        (`_C.set_grad_arena`): its backward then writes the gradients straight into the buffer.
+        Returns False (and changes nothing) for packages without that extension (the reference)."""
         fn = getattr(getattr(rasterizer_module, "_C", None), "set_grad_arena", None)
         if fn is None or not self.is_cuda:
             return False
-        fn(self.flat)
+        fn(self.flat, self.mode == "factorized_sh")
         self._attached = rasterizer_module
         return True
 
     def detach(self):
-        mod = getattr(self, "_attached", None)
-        if mod is not None:
-            mod._C.set_grad_arena(torch.Tensor())
+        if self._attached is not None:
+            self._attached._C.set_grad_arena(torch.Tensor(), False)
             self._attached = None
+
+    def views(self):
+        """Per-parameter reduced gradients (valid after wait())."""
+        out = {k: self.flat[o:o + n].view(shape) for k, (o, n, shape) in self.slices.items()}
+        if self.mode == "factorized_sh":
+            out["shs"] = self.sh_sum
+        return out
+
+    def pack(self, grads, masked_color=None, campos=None):
+        for k, (o, n, _shape) in self.slices.items():
+            g = grads.get(k)
+            self.flat[o:o + n].copy_(g.reshape(-1) if g is not None else 0)
+        if self.mode == "factorized_sh":
+            self.flat[:3 * self.P].copy_(masked_color.reshape(-1))
+            self.flat[3 * self.P:3 * self.P + 3].copy_(campos.reshape(-1)[:3])
 
     def _aliases_flat(self, grads):
         lo = self.flat.data_ptr()
@@ -82,36 +144,59 @@ class SceneGradReducer:
                 return False
         return True
 
-    def reduce_async(self, grads=None):
-        """Pack (unless the gradients already live in the flat buffer, see attach()) and launch
-        the single all-reduce.  Returns immediately; call wait() before reading views()."""
-        if grads is not None and not self._aliases_flat(grads):
-            self.pack(grads)
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            self._work = None
+    # ---- the exchange -------------------------------------------------------------------------
+    def _world(self):
+        if not dist.is_available() or not dist.is_initialized():
+            return 1
+        return dist.get_world_size(self.group)
+
+    def _exchange(self):
+        world = self._world()
+        if self.mode == "allreduce":
+            if world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                self.flat.div_(world)
             return
+        head = self.flat[:self.head]
+        if self.gathered is None or self.gathered.shape[0] != world:
+            self.gathered = torch.empty(world, self.head, dtype=torch.float32, device=self.flat.device)
+        if world > 1:
+            dist.all_gather_into_tensor(self.gathered.view(-1), head, group=self.group)
+            dist.all_reduce(self.flat[self.head:], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.gathered[0].copy_(head)
+        if self.is_cuda and self._attached is not None:
+            self.sh_sum = self._attached._C.sh_grad_from_views(self.means3D.detach(), self.gathered,
+                                                               self.sh_degree, self.M)
+        elif self.is_cuda:
+            raise RuntimeError("factorized_sh on CUDA needs attach() to a B200-native rasterizer package")
+        else:
+            self.sh_sum = sh_grad_from_views_torch(self.means3D.detach(), self.gathered, self.sh_degree, self.M)
+        if self.average:
+            self.flat[self.head:].div_(world)
+            self.sh_sum.div_(world)
+
+    def reduce_async(self, grads=None, masked_color=None, campos=None):
+        """Pack (unless the gradients already live in the flat buffer, see attach()) and launch the
+        exchange.  Returns immediately on CUDA; call wait() before reading views()."""
+        if grads is not None and not (self._attached is not None and self._aliases_flat(grads)):
+            self.pack(grads, masked_color, campos)
         if self.is_cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-                if self.average:
-                    self.flat.div_(dist.get_world_size(self.group))
+                self._exchange()
                 self._done = torch.cuda.Event()
                 self._done.record(self.stream)
         else:
-            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._exchange()
 
     def wait(self):
-        if self.is_cuda:
-            if self._done is not None:
-                torch.cuda.current_stream().wait_event(self._done)
-                self._done = None
-        elif self._work is not None:
-            self._work.wait()
-            self._work = None
-            if self.average:
-                self.flat.div_(dist.get_world_size(self.group))
+        if self.is_cuda and self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)
+            self._done = None
         return self.views()
 
     def bytes_per_step(self):
+        """fp32 bytes this rank contributes to the exchange per step."""
         return self.numel * 4

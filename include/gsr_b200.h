@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_B200_ABI_VERSION 1
+#define GSR_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSR_API __attribute__((visibility("default")))
@@ -99,6 +99,16 @@ GSR_API int gsr_get_option(const char* key);
 GSR_API int gsr_stage_times(double* ms, long long* scopes, long long* launches, int reset);
 GSR_API const char* gsr_stage_name(int stage);
 
+/* Optional extras of the backward calls (not part of the reference surface; pass NULL for none).
+ * They serve view-level data parallelism: dL/dSH of a view is the rank-1 product
+ * basis_k(view direction) x dL_dcolor_masked[c], so ranks can exchange 3 floats per Gaussian and view
+ * instead of 3*M and rebuild the summed dL/dSH locally with gsr_sh_grad_from_views(). */
+typedef struct gsr_backward_extras {
+  float* dL_dcolor_masked; /* out [P,3]: dL/dcolor with the channels clamped at 0 by the forward zeroed
+                              (0 for culled Gaussians); NULL = not wanted; needs SH colours */
+  int skip_sh_grad;        /* 1: do not write dL_dsh */
+} gsr_backward_extras;
+
 /* ---- light variant ---------------------------------------------------------------------- */
 
 /* replaces L/cuda_rasterizer/rasterizer.h:31-63  (Rasterizer::forward).
@@ -142,7 +152,7 @@ GSR_API int gsr_light_backward(
     float* dL_dscale, float* dL_drot,
     int debug, const float* perspec_matrix, float* dL_dview,
     const float* gt_depth, int track_off, int map_off,
-    float* scratch, void* stream);
+    float* scratch, void* stream, const gsr_backward_extras* extras);
 
 /* ---- full variant ----------------------------------------------------------------------- */
 
@@ -181,7 +191,17 @@ GSR_API int gsr_full_backward(
     float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
     float* dL_dscale, float* dL_drot,
     const float* perspec_matrix, float* dL_dview,
-    const float* gt_depth, float* scratch, void* stream);
+    const float* gt_depth, float* scratch, void* stream, const gsr_backward_extras* extras);
+
+/* Sum over `nviews` camera views of dL/dSH, rebuilt from each view's masked colour gradient:
+ *   dL_dsh[g][k][c] = sum_v basis_k(normalize(means3D[g] - campos_v)) * dR_v[g][c],  k < (D+1)^2,
+ * zero for k >= (D+1)^2.  dR_v = dR_all + v * view_stride (floats), campos_v = campos_all +
+ * v * campos_stride (floats).  Same value as adding the per-view dL_dsh outputs of the backward
+ * calls (up to summation order).  Not part of the reference surface. */
+GSR_API int gsr_sh_grad_from_views(int P, int D, int M, const float* means3D, int nviews,
+                                   const float* dR_all, size_t view_stride,
+                                   const float* campos_all, size_t campos_stride,
+                                   float* dL_dsh, void* stream);
 
 /* replaces Rasterizer::markVisible (rasterizer.h:24-29): present[i] = view-space z > 0.2.
  * `present` is one byte per Gaussian (0/1). */

@@ -65,6 +65,58 @@ def test_flat_gradient_allreduce_world2():
     assert res[0][2] == [0, 2, 4] and res[1][2] == [1, 3]
 
 
+def _worker_fact(rank, world, port, P, M, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as ge
+    dp = ge.load_dp_module()
+    shapes = dict(means3D=(P, 3), shs=(P, M, 3), opacities=(P, 1), scales=(P, 3), rotations=(P, 4))
+    means = torch.randn(P, 3, generator=torch.Generator().manual_seed(7)) + torch.tensor([0.0, 0.0, 4.0])
+
+    def rank_data(r):
+        g = torch.Generator().manual_seed(200 + r)
+        grads = {k: torch.randn(*s, generator=g) for k, s in shapes.items() if k != "shs"}
+        dR = torch.randn(P, 3, generator=g)
+        dR[::5] = 0.0  # culled in this view
+        campos = torch.randn(3, generator=g) * 0.3
+        return grads, dR, campos
+
+    grads, dR, campos = rank_data(rank)
+    red = dp.SceneGradReducer(shapes, "cpu", mode="factorized_sh", means3D=means, sh_degree=3)
+    assert red.numel == 14 * P + 4
+    red.reduce_async(grads, masked_color=dR, campos=campos)
+    views = red.wait()
+    ok = True
+    exp_sh = torch.zeros(P, M, 3)
+    for r in range(world):
+        g_r, dR_r, cp_r = rank_data(r)
+        d = means - cp_r
+        d = d / d.norm(dim=1, keepdim=True)
+        exp_sh += dp.sh_basis(d, 3)[:, :, None] * dR_r[:, None, :]
+    ok = ok and torch.allclose(views["shs"], exp_sh, atol=1e-5)
+    for k in ("means3D", "opacities", "scales", "rotations"):
+        exp = sum(rank_data(r)[0][k] for r in range(world))
+        ok = ok and torch.allclose(views[k], exp, atol=1e-6)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_factorized_sh_exchange_world2():
+    world, P, M = 2, 100, 16
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fact, args=(r, world, port, P, M, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
 def test_single_process_passthrough():
     import __graft_entry__ as ge
     dp = ge.load_dp_module()
