@@ -16,3 +16,7 @@ print("N=$n: %.1f fps  %.3f ms/step  e2e %.1f fps" % (a["value"], a["ms_per_step
 PY
 done
 grep -h "arena" gpurun_out/scale/*.err | head -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 \
+  bench.py --gpus 8 --steps 20 --warmup 5 --dp-mode allreduce > gpurun_out/scale/n8_allreduce.json 2> gpurun_out/scale/n8_allreduce.err
+python -c "
+import json; a=json.load(open('gpurun_out/scale/n8_allreduce.json')); print('N=8 allreduce: %.1f fps  %.3f ms/step' % (a['value'], a['ms_per_step']))"
