@@ -154,7 +154,10 @@ class Frame:
         self.h_view, self.h_proj, self.h_campos = pin(cam.viewmatrix), pin(cam.projmatrix), pin(cam.campos)
         self.h_gt = pin(scene.gt_depth)
         self.h_cots = [pin(cot[0])] + [pin(c) for c in cot[1]]
-        self.h_result = torch.empty(17, dtype=torch.float32).pin_memory()
+        self.h_results = [torch.empty(17, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.res_ev = [None, None]
+        self.e2e_steps = 0
+        self.pending = None
         self.cam, self.scene = cam, scene
         self.rast = self._rasterizer(cam.viewmatrix.to(device), cam.projmatrix.to(device), cam.campos.to(device))
         self.h2d_bytes = sum(t.numel() * 4 for t in [self.h_view, self.h_proj, self.h_campos, self.h_gt] + self.h_cots)
@@ -191,37 +194,55 @@ class Frame:
     def grads(self):
         return {k: v.grad for k, v in self.params.items()}
 
-    def step_e2e(self):
-        """Same frame with the per-frame inputs coming from pinned host memory and the result
-        (loss, dL/dviewmatrix) going back to the host."""
+    def _upload(self):
+        """Enqueue the H2D copies of ONE step's per-frame inputs (camera, gt depth, cotangents) from
+        pinned host memory on the copy stream; returns the device tensors and a completion event."""
         torch, dev = self.torch, self.device
-        main = torch.cuda.current_stream()
-        view = self.h_view.to(dev, non_blocking=True).requires_grad_(True)
-        proj = self.h_proj.to(dev, non_blocking=True)
-        campos = self.h_campos.to(dev, non_blocking=True)
-        gt = self.h_gt.to(dev, non_blocking=True)
-        # the cotangents are only needed by the backward: upload them on a copy stream while the
-        # forward runs (what an input pipeline does), and join before the backward
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=dev)
-        self.copy_stream.wait_stream(main)
         with torch.cuda.stream(self.copy_stream):
-            cots = [c.to(dev, non_blocking=True) for c in self.h_cots]
-        rast = self._rasterizer(view.detach(), proj, campos)
+            d = dict(view=self.h_view.to(dev, non_blocking=True), proj=self.h_proj.to(dev, non_blocking=True),
+                     campos=self.h_campos.to(dev, non_blocking=True), gt=self.h_gt.to(dev, non_blocking=True),
+                     cots=[c.to(dev, non_blocking=True) for c in self.h_cots])
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return d, ev
+
+    def step_e2e(self):
+        """Same frame with the per-frame inputs coming from pinned host memory and the result
+        (loss, dL/dviewmatrix) going back to the host, organised like an input pipeline: every step
+        uploads one step's inputs (the NEXT step's, on a copy stream, while this step computes) and
+        reads one step's result (asynchronously into a pinned double buffer; the host consumes the
+        value one step later).  Exactly one upload and one result read-back per step."""
+        torch, dev = self.torch, self.device
+        main = torch.cuda.current_stream()
+        if self.pending is None:
+            self.pending = self._upload()
+        inp, ev = self.pending
+        self.pending = self._upload()
+        main.wait_event(ev)
+        for t in [inp["view"], inp["proj"], inp["campos"], inp["gt"]] + inp["cots"]:
+            t.record_stream(main)
+        view = inp["view"].requires_grad_(True)
+        rast = self._rasterizer(view.detach(), inp["proj"], inp["campos"])
         p = self.params
         res = rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"], shs=p["shs"],
-                   scales=p["scales"], rotations=p["rotations"], viewmatrix=view, gt_depth=gt)
+                   scales=p["scales"], rotations=p["rotations"], viewmatrix=view, gt_depth=inp["gt"])
         outs = self._outs(res)
-        main.wait_stream(self.copy_stream)
-        for c in cots:
-            c.record_stream(main)
-        torch.autograd.backward(outs, cots)
+        torch.autograd.backward(outs, inp["cots"])
         with torch.no_grad():
-            loss = sum((o * c).sum() for o, c in zip(outs, cots))
+            loss = sum((o * c).sum() for o, c in zip(outs, inp["cots"]))
             packed = torch.cat([loss.reshape(1), view.grad.reshape(16)])
-        self.h_result.copy_(packed, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the result on the host
-        return float(self.h_result[0])
+        slot = self.e2e_steps & 1
+        self.e2e_steps += 1
+        value = None
+        if self.res_ev[slot] is not None:      # result of two steps ago: complete long since
+            self.res_ev[slot].synchronize()
+            value = float(self.h_results[slot][0])
+        self.h_results[slot].copy_(packed, non_blocking=True)
+        self.res_ev[slot] = torch.cuda.Event()
+        self.res_ev[slot].record(main)
+        return value
 
 
 def timed_region(torch, dist, fn, steps, world):

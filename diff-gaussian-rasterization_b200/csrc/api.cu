@@ -15,7 +15,7 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -210,6 +210,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "stage_timing")) return &g_opts.stage_timing;
   if (!strcmp(key, "tile_sort")) return &g_opts.tile_sort;
   if (!strcmp(key, "bwd_packed")) return &g_opts.bwd_packed;
+  if (!strcmp(key, "async_binning")) return &g_opts.async_binning;
   return nullptr;
 }
 

@@ -10,6 +10,8 @@
 //
 // Roofline: HBM. Algorithmic bytes: scan 8*P; emit 20*P + 12*N; sort (24*passes + 8)*N;
 // ranges 8*N + 8*tiles.
+#include <atomic>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -195,7 +197,10 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
                                        const uint32_t* __restrict__ tiles_touched,
                                        const uint2* __restrict__ rects, int grid_x,
                                        uint32_t* __restrict__ tile_fill,
-                                       uint64_t* __restrict__ entries) {
+                                       uint64_t* __restrict__ entries, uint32_t capacity) {
+  // `capacity` = entries the buffer can hold.  It only bites when the buffer was sized from the
+  // previous frame's count (speculative launch, see run_binning) and this frame has more: the
+  // surplus is dropped and the host, which sees the real count, redoes the binning.
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t n = (idx < P) ? tiles_touched[idx] : 0u;
@@ -218,7 +223,8 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
     const uint64_t e = ((uint64_t)e_hi << 32) | e_lo;
     for (uint32_t q = lane; q < total; q += 32) {
       const uint32_t t = (y0 + q / w) * (uint32_t)grid_x + x0 + q % w;
-      entries[atomicAdd(tile_fill + t, 1u)] = e;
+      const uint32_t slot = atomicAdd(tile_fill + t, 1u);
+      if (slot < capacity) entries[slot] = e;
     }
   }
   if (n != 0u && n <= kWide) {
@@ -231,7 +237,7 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
       if (u < n) slots[u] = atomicAdd(tile_fill + (y0 + u / w) * (uint32_t)grid_x + x0 + u % w, 1u);
 #pragma unroll
     for (uint32_t u = 0; u < kWide; ++u)
-      if (u < n) entries[slots[u]] = entry;
+      if (u < n && slots[u] < capacity) entries[slots[u]] = entry;
   }
 }
 
@@ -326,12 +332,14 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, const uint64_t* _
 
 __global__ void __launch_bounds__(kTileSortThreads)
 sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
-                  uint32_t* __restrict__ vals) {
+                  uint32_t* __restrict__ vals, uint32_t capacity, int smem_entries) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
   uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem_raw);
   const uint2 range = ranges[blockIdx.x];
   const int n = (int)(range.y - range.x);
   if (n == 0) return;
+  // speculative launch with too small a buffer / too little shared memory: the host redoes it
+  if (range.y > capacity || n > smem_entries) return;
   const int tid = threadIdx.x;
   const uint64_t* in = entries + range.x;
   uint32_t* out = vals + range.x;
@@ -353,6 +361,57 @@ sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__
   }
 }
 
+// Pinned read-back slots for the duplicate count (so the copy is truly asynchronous) and the
+// sizes seen on the previous frame (to size this frame's binning buffer before the count is known).
+struct CountSlots {
+  static constexpr int kSlots = 32;
+  uint32_t* host = nullptr;  // [kSlots][4] pinned
+  cudaEvent_t ev[kSlots];
+  std::atomic<unsigned> next{0};
+  std::atomic<uint32_t> hint_entries{0}, hint_longest{0};
+  bool ok = false;
+  CountSlots() {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host), sizeof(uint32_t) * 4 * kSlots, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    for (int i = 0; i < kSlots; ++i)
+      if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    ok = true;
+  }
+};
+CountSlots& count_slots() {
+  static CountSlots* s = new CountSlots();  // leaked on purpose (outlives static destruction)
+  return *s;
+}
+
+int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgState& img, BinState& b,
+                     uint32_t capacity, uint32_t longest_cap, bool debug, cudaStream_t stream) {
+  const int tiles = cam.grid_x * cam.grid_y;
+  {
+    StageScope st(ST_EMIT, stream);
+    scatter_entries_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+        P, g.rec, g.tiles_touched, g.rect, cam.grid_x, img.tile_fill, b.keys_unsorted, capacity);
+    GSR_LAUNCH_OK(debug, stream);
+  }
+  {
+    StageScope st(ST_SORT, stream);
+    int p = kTileSortThreads;  // the register network exchanges 256*E entries through smem
+    while (p < (int)longest_cap) p <<= 1;
+    const size_t smem = (size_t)p * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kTileSortCap * (int)sizeof(uint64_t)));
+      attr_set = true;
+    }
+    sort_tiles_kernel<<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals,
+                                                                capacity, p);
+    GSR_LAUNCH_OK(debug, stream);
+  }
+  return GSR_OK;
+}
+
 }  // namespace
 
 int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gsr_alloc_fn alloc,
@@ -361,6 +420,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
   const int tiles = cam.grid_x * cam.grid_y;
   const bool tile_local = options().tile_sort != 0;
   uint32_t N = 0, longest = 0;
+  bool sorted_speculatively = false;
 
   if (tile_local) {
     {
@@ -370,13 +430,55 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
                                                 g.counters);
       GSR_LAUNCH_OK(debug, stream);
     }
-    // The one host<->device synchronisation of the forward: the duplicate count sizes the
-    // binning buffer (the reference blocks in the same place, rasterizer_impl.cu:287).
+    // The one host<->device synchronisation of the forward: the duplicate count sizes the binning
+    // buffer and is returned to the caller (the reference blocks in the same place,
+    // rasterizer_impl.cu:287).  To keep the GPU busy while the host waits, the count is copied into
+    // pinned memory asynchronously and — when a previous frame left a size estimate — the scatter
+    // and the per-tile sort are enqueued first, on a buffer sized from that estimate; the kernels
+    // are guarded, and if the estimate turns out too small the binning is simply redone.
+    CountSlots& cs = count_slots();
+    const uint32_t hint_n = cs.hint_entries.load(), hint_l = cs.hint_longest.load();
+    const bool speculate = cs.ok && options().async_binning != 0 && hint_n > 0 && hint_l <= (uint32_t)kTileSortCap;
     uint32_t h[4] = {0, 0, 0, 0};
-    GSR_CUDA_OK(cudaMemcpyAsync(h, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    GSR_CUDA_OK(cudaStreamSynchronize(stream));
+    if (cs.ok) {
+      const unsigned slot = cs.next.fetch_add(1) % CountSlots::kSlots;
+      uint32_t* hp = cs.host + 4 * slot;
+      GSR_CUDA_OK(cudaMemcpyAsync(hp, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+      GSR_CUDA_OK(cudaEventRecord(cs.ev[slot], stream));
+      uint32_t cap = 0, lcap = 0;
+      if (speculate) {
+        cap = hint_n + hint_n / 4 + 4096;
+        lcap = hint_l * 2 < (uint32_t)kTileSortThreads ? (uint32_t)kTileSortThreads : hint_l * 2;
+        if (lcap > (uint32_t)kTileSortCap) lcap = kTileSortCap;
+        const size_t need = BinState::carve(b, nullptr, cap, 0, false);
+        char* chunk = alloc(alloc_ctx, need);
+        if (chunk == nullptr) { set_error("binning allocator returned NULL for %zu bytes", need); return GSR_E_ALLOC; }
+        BinState::carve(b, chunk, cap, 0, false);
+        const int rc = launch_tile_sort(cam, P, g, img, b, cap, lcap, debug, stream);
+        if (rc != GSR_OK) return rc;
+      }
+      GSR_CUDA_OK(cudaEventSynchronize(cs.ev[slot]));
+      h[0] = hp[0]; h[2] = hp[2];
+      if (speculate) {
+        int p = kTileSortThreads;
+        while (p < (int)lcap) p <<= 1;
+        sorted_speculatively = h[0] <= cap && h[2] <= (uint32_t)p;
+        if (!sorted_speculatively) {
+          // estimate too small: reset the scatter cursors (the scan rewrites them) and fall through
+          StageScope st(ST_SCAN, stream, 1);
+          scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
+                                                    g.counters);
+          GSR_LAUNCH_OK(debug, stream);
+        }
+      }
+    } else {
+      GSR_CUDA_OK(cudaMemcpyAsync(h, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+      GSR_CUDA_OK(cudaStreamSynchronize(stream));
+    }
     N = h[0];
     longest = h[2];
+    cs.hint_entries.store(N);
+    cs.hint_longest.store(longest);
   } else {
     StageScope st(ST_SCAN, stream);
     GSR_CUDA_OK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_bytes, g.tiles_touched,
@@ -389,6 +491,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     GSR_CUDA_OK(cudaStreamSynchronize(stream));
   }
   *num_rendered = (int)N;
+  if (sorted_speculatively) return GSR_OK;
 
   const bool use_tile_sort = tile_local && longest <= (uint32_t)kTileSortCap;
   const int end_bit = 32 + bits_for((uint32_t)tiles);
@@ -403,27 +506,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
 
   if (use_tile_sort) {
     if (N == 0) return GSR_OK;  // ranges were written (all empty) by scan_tiles_kernel
-    {
-      StageScope st(ST_EMIT, stream);
-      scatter_entries_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
-          P, g.rec, g.tiles_touched, g.rect, cam.grid_x, img.tile_fill, b.keys_unsorted);
-      GSR_LAUNCH_OK(debug, stream);
-    }
-    {
-      StageScope st(ST_SORT, stream);
-      int p = kTileSortThreads;  // the register network exchanges 256*E entries through smem
-      while (p < (int)longest) p <<= 1;
-      const size_t smem = (size_t)p * sizeof(uint64_t);
-      static bool attr_set = false;
-      if (!attr_set) {
-        GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kTileSortCap * (int)sizeof(uint64_t)));
-        attr_set = true;
-      }
-      sort_tiles_kernel<<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals);
-      GSR_LAUNCH_OK(debug, stream);
-    }
-    return GSR_OK;
+    return launch_tile_sort(cam, P, g, img, b, N, longest, debug, stream);
   }
 
   // ---- radix path (reference structure; also the fallback for very long tile lists) ----

@@ -46,6 +46,7 @@ struct Options {
   int stage_timing;
   int tile_sort;
   int bwd_packed;
+  int async_binning;
 };
 Options& options();
 

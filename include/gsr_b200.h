@@ -84,6 +84,11 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *   "bwd_packed"    backward blend kernel: 1 = two pixels per lane, packed fp32x2 arithmetic, 8x8
  *                   pixel blocks; 0 = one pixel per lane, 8x4 blocks; 2 (default) = pick per call
  *                   from the number of duplicates per Gaussian (same results up to summation order).
+ *   "async_binning" 1 (default): the forward sizes the binning buffer from the previous frame's
+ *                   duplicate count (+25 %) and enqueues the scatter and the per-tile sort before
+ *                   the host has read this frame's count, so the GPU does not idle during the
+ *                   read-back (guarded kernels; the binning is redone when the estimate was too
+ *                   small); 0: wait for the count first, exact buffer size.
  * Returns the previous value, or GSR_E_INVALID for an unknown key. */
 GSR_API int gsr_set_option(const char* key, int value);
 GSR_API int gsr_get_option(const char* key);

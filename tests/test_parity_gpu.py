@@ -338,6 +338,36 @@ def test_packed_and_scalar_backward_kernels_agree(built, variant):
         assert rel < 2e-4 and bad < 1e-3, (k, rel, bad)
 
 
+def test_speculative_binning_overflow_is_redone(built):
+    """async_binning sizes the binning buffer from the previous frame: a small frame followed by a
+    much larger one (and by one with much longer tile lists) must redo the binning and stay exact."""
+    sc = ge.load_scene_module()
+    mod = built.load_variant("light")
+    cam_s = sc.make_camera(64, 48)
+    small = sc.make_scene(300, cam_s, (1.0, 3.0), seed=46)
+    cam_b = sc.make_camera(320, 240)
+    big = sc.make_scene(30000, cam_b, (2.0, 14.0), seed=47)
+    cot_s, cot_b = sc.make_cotangents(cam_s, 3), sc.make_cotangents(cam_b, 3)
+    pu.set_option("async_binning", 0)
+    try:
+        ref_o, ref_g = pu.run_variant(mod, "light", cam_b, big, cot_b)
+    finally:
+        pu.set_option("async_binning", 1)
+    for _ in range(2):
+        pu.run_variant(mod, "light", cam_s, small, cot_s)      # leaves a tiny estimate behind
+        o, g = pu.run_variant(mod, "light", cam_b, big, cot_b)  # overflows it
+        for k in ref_o:
+            if k != "gau_uncertainty":
+                assert np.array_equal(o[k], ref_o[k]), k
+        for k in ref_g:
+            rel, _ = pu.grad_mismatch(g[k], ref_g[k], rtol=1e-4)
+            assert rel < 1e-4, k
+    o, g = pu.run_variant(mod, "light", cam_b, big, cot_b)      # estimate now fits: speculative path
+    for k in ref_o:
+        if k != "gau_uncertainty":
+            assert np.array_equal(o[k], ref_o[k]), k
+
+
 def test_very_long_tile_list_falls_back_to_radix(built):
     """More than 8192 entries in one tile: the frame takes the radix path and still matches the oracle."""
     sc = ge.load_scene_module()
