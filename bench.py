@@ -137,8 +137,9 @@ def build_inputs(ge, cfg_name, variant, device, view_seed, pin=False):
 class Frame:
     """One camera view's fwd+bwd through the public Python API of `mod`."""
 
-    def __init__(self, mod, variant, cam, scene, cot, device):
+    def __init__(self, mod, variant, cam, scene, cot, device, track_off=False, map_off=False):
         import torch
+        self.track_off, self.map_off = track_off, map_off
         self.torch = torch
         self.mod, self.variant, self.device = mod, variant, device
         d = lambda t, rg=False: t.to(device).clone().requires_grad_(rg)
@@ -171,7 +172,7 @@ class Frame:
                   bg=scene.bg.to(dev), scale_modifier=1.0, viewmatrix=view, projmatrix=proj, sh_degree=3,
                   campos=campos, prefiltered=False, perspec_matrix=cam.perspec_matrix.to(dev))
         if self.variant == "light":
-            kw.update(debug=False, track_off=False, map_off=False)
+            kw.update(debug=False, track_off=self.track_off, map_off=self.map_off)
         return self.mod.GaussianRasterizer(self.mod.GaussianRasterizationSettings(**kw))
 
     def _outs(self, res):
@@ -314,6 +315,8 @@ def main():
     ap.add_argument("--variant", default="full", choices=["light", "full"])
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU oracle sample (0 = skip)")
     ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--track-off", action="store_true", help="-light only: mapping mode (no pose gradient)")
+    ap.add_argument("--map-off", action="store_true", help="-light only: tracking mode (pose gradient only)")
     ap.add_argument("--dp-mode", default="factorized_sh", choices=["allreduce", "factorized_sh"],
                     help="gradient exchange at N > 1 (diff-gaussian-rasterization_b200/dp.py)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (gsr_set_option)")
@@ -363,7 +366,9 @@ def main():
 
     mod = ge.load_reference(a.variant) if a.impl == "reference" else ge.load_variant(a.variant)
     sc, cam, scene, cot = build_inputs(ge, a.config, a.variant, device, rank)
-    frame = Frame(mod, a.variant, cam, scene, cot, device)
+    frame = Frame(mod, a.variant, cam, scene, cot, device, a.track_off, a.map_off)
+    if a.track_off or a.map_off:
+        workload += " [%s]" % ("tracking: map_off" if a.map_off else "mapping: track_off")
 
     reducer = None
     if world > 1:

@@ -382,7 +382,7 @@ int gsr_light_backward(
   if (want_gauss || want_pose) {
     BlendGrads cot{dL_dpix, dL_dpix_depth, dL_dpix_median_depth, dL_dpix_depth_var};
     rc = launch_render_bwd(kLight, cam, g, b, img, background, gt_depth, alphas, cot, acc, P, R,
-                           debug != 0, s);
+                           /*pose_only=*/!want_gauss, debug != 0, s);
     if (rc != GSR_OK) return rc;
   }
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
@@ -431,7 +431,7 @@ int gsr_full_backward(
     GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
   }
   BlendGrads cot{dL_dpix, dL_dpix_depth, nullptr, dL_dpix_uncertainty};
-  rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, s);
+  rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, false, s);
   if (rc != GSR_OK) return rc;
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
                    dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr};

@@ -445,7 +445,8 @@ struct BlendGrads {       // per-pixel cotangents
 int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
                       const ImgState& img, const float* bg, const float* gt_depth,
                       const float* alphas /*light*/, const BlendGrads& cot, float* acc,
-                      int num_gaussians, int num_entries, bool debug, cudaStream_t stream);
+                      int num_gaussians, int num_entries, bool pose_only, bool debug,
+                      cudaStream_t stream);
 
 struct GaussGradOut {
   float* dL_dmean2D; float* dL_dconic; float* dL_dopacity; float* dL_dcolor; float* dL_ddepth;

@@ -54,7 +54,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const int base = blockIdx.x * kBwdThreads;
   const int idx = base + threadIdx.x;
   const int row = M * 3 + 1;
-  const bool use_sh = (shs != nullptr) && want_gauss;
+  const bool use_sh = (shs != nullptr) && want_gauss;           // SH coefficients staged in
+  const bool sh_out = (shs != nullptr) && out.dL_dsh != nullptr;  // dL/dSH slab staged out
   const int nvalid = min(kBwdThreads, P - base);
   const int nfloats = nvalid * M * 3;
 
@@ -70,7 +71,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const bool live = idx < P && radii[idx] > 0;
   float* my_sh = sh_smem + threadIdx.x * row;
 
-  if (idx < P && !live && want_gauss) {
+  // culled Gaussians — and, in -light's tracking mode (map_off), all of them — get exact zeros
+  if (idx < P && (!live || !want_gauss)) {
     st3(out.dL_dmean2D, idx, 0.f, 0.f, 0.f);
     if (out.dL_dconic) {
       reinterpret_cast<float4*>(out.dL_dconic)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -86,7 +88,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     }
     st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
     if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (use_sh) {
+    if (sh_out) {
       for (int k = 0; k < M * 3; ++k) my_sh[k] = 0.f;
     }
   }
@@ -402,7 +404,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   }
 
   // coalesced store of the block's dL/dSH slab
-  if (use_sh && out.dL_dsh != nullptr) {
+  if (sh_out) {
     __syncthreads();
     smem_to_rows<MT * 3>(out.dL_dsh + (size_t)base * M * 3, sh_smem, nvalid, M * 3, threadIdx.x,
                          kBwdThreads);
@@ -465,30 +467,15 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
                           const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
                           cudaStream_t stream) {
   const int blocks = (P + kBwdThreads - 1) / kBwdThreads;
-  const size_t smem = (shs != nullptr && want_gauss) ? sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1) : 0;
+  const size_t smem = (shs != nullptr) ? sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1) : 0;
   const float* cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
   StageScope st(ST_PRE_BWD, stream, 2);
-  if (!want_gauss) {
-    // light + map_off: every per-Gaussian gradient is zero (light backward.cu:593,609,654,666;
-    // rasterizer_impl.cu:467)
-    auto zero = [&](float* p, size_t n) -> cudaError_t {
-      return p ? cudaMemsetAsync(p, 0, n * sizeof(float), stream) : cudaSuccess;
-    };
-    GSR_CUDA_OK(zero(out.dL_dmean2D, 3 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dconic, 4 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dopacity, (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dcolor, 3 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dcolor_masked, 3 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_ddepth, (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dmean3D, 3 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dcov3D, 6 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_dsh, 3 * (size_t)P * (size_t)M));
-    GSR_CUDA_OK(zero(out.dL_dscale, 3 * (size_t)P));
-    GSR_CUDA_OK(zero(out.dL_drot, 4 * (size_t)P));
-  } else if (shs == nullptr && out.dL_dsh != nullptr && M > 0) {
+  // With want_gauss == false (-light, map_off: light backward.cu:593,609,654,666;
+  // rasterizer_impl.cu:467) the kernel itself writes the zero gradients: no memset passes.
+  if (shs == nullptr && out.dL_dsh != nullptr && M > 0) {
     GSR_CUDA_OK(cudaMemsetAsync(out.dL_dsh, 0, sizeof(float) * 3 * (size_t)P * (size_t)M, stream));
   }
-  if (want_gauss || want_pose) {
+  {
 #define GSR_PRE_BWD(V, MT)                                                                       \
   cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                        cudaSharedmemCarveoutMaxShared);                                          \

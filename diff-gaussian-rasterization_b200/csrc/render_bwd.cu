@@ -29,13 +29,23 @@ constexpr int kRedVals = 14;    // accumulator slots reduced per (warp, Gaussian
 constexpr int kRedStride = 36;  // floats per slot row in shared memory (144 B: 16-byte aligned rows
                                 // whose bank offsets rotate by 4, conflict-free per quarter warp)
 
+// Reduced slot sets: all 14 accumulator slots, or — for -light's tracking mode (map_off: only the
+// pose gradient is wanted) — just the three the pose contraction reads.
+template <bool POSE_ONLY>
+struct RedSet {
+  static constexpr int N = POSE_ONLY ? 3 : kRedVals;
+  __device__ static constexpr int slot(int q) {
+    return POSE_ONLY ? (q == 0 ? (int)ACC_MX : (q == 1 ? (int)ACC_MY : (int)ACC_PD)) : q;
+  }
+};
+
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
-template <int VARIANT>
+template <int VARIANT, bool POSE_ONLY>
 __global__ void __launch_bounds__(kTileThreads)
 render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
@@ -223,12 +233,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       }
       // warp reduction through shared memory: every lane stores its column, 28 lanes each add
       // half a row (4 x LDS.128), pairs combine with one shuffle, 14 lanes issue one coalesced red
+      using RS = RedSet<POSE_ONLY>;
       float* red = s_red[warp];
 #pragma unroll
-      for (int q = 0; q < kRedVals; ++q) red[q * kRedStride + lane] = v[q];
+      for (int q = 0; q < RS::N; ++q) red[q * kRedStride + lane] = v[RS::slot(q)];
       __syncwarp();
       float sum = 0.f;
-      if (lane < 2 * kRedVals) {
+      if (lane < 2 * RS::N) {
         const float4* row = reinterpret_cast<const float4*>(red + (lane >> 1) * kRedStride + (lane & 1) * 16);
         const float4 a = row[0], b = row[1], c = row[2], d = row[3];
         sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
@@ -236,10 +247,10 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       }
       // lane (2q + h) now holds slot q summed over half warp h, i.e. over that half's own entry
       const int j_lo = __shfl_sync(0xffffffffu, j, 0), j_hi = __shfl_sync(0xffffffffu, j, 16);
-      if (lane < 2 * kRedVals) {
+      if (lane < 2 * RS::N) {
         const int h = lane & 1;
         if ((vmask >> (16 * h)) & 0xFFFFu)
-          atomicAdd(acc + (size_t)s_id[h ? j_hi : j_lo] * kAccStride + (lane >> 1), sum);
+          atomicAdd(acc + (size_t)s_id[h ? j_hi : j_lo] * kAccStride + RS::slot(lane >> 1), sum);
       }
       __syncwarp();
     }
@@ -309,7 +320,7 @@ __device__ __forceinline__ unsigned block_mask4(const float4& r0, const float4& 
   return mask;
 }
 
-template <int VARIANT>
+template <int VARIANT, bool POSE_ONLY>
 __global__ void __launch_bounds__(kBwd2Threads, 8)
 render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                    const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
@@ -506,20 +517,22 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
         v[ACC_PGY] = f2_mul(q, dy2);
       }
       // warp reduction through shared memory (both pixels of a lane are added first)
+      using RS = RedSet<POSE_ONLY>;
       float* red = s_red[warp];
 #pragma unroll
-      for (int qn = 0; qn < kRedVals; ++qn) red[qn * kRedStride + lane] = f2_lo(v[qn]) + f2_hi(v[qn]);
+      for (int qn = 0; qn < RS::N; ++qn)
+        red[qn * kRedStride + lane] = f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]);
       __syncwarp();
       float sum = 0.f;
-      if (lane < 2 * kRedVals) {
+      if (lane < 2 * RS::N) {
         const float4* row = reinterpret_cast<const float4*>(red + (lane >> 1) * kRedStride + (lane & 1) * 16);
         const float4 a = row[0], b = row[1], c = row[2], d = row[3];
         sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
               (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
       }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      if (lane < 2 * kRedVals && (lane & 1) == 0)
-        atomicAdd(acc + (size_t)s_id[j] * kAccStride + (lane >> 1), sum);
+      if (lane < 2 * RS::N && (lane & 1) == 0)
+        atomicAdd(acc + (size_t)s_id[j] * kAccStride + RS::slot(lane >> 1), sum);
       __syncwarp();
     }
   }
@@ -530,7 +543,7 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
 int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
                       const ImgState& img, const float* bg, const float* gt_depth,
                       const float* alphas, const BlendGrads& cot, float* acc, int num_gaussians,
-                      int num_entries, bool debug, cudaStream_t stream) {
+                      int num_entries, bool pose_only, bool debug, cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_BWD, stream);
   // auto (2): the packed kernel works on 8x8 pixel blocks and wins when splats are large enough to
@@ -538,29 +551,25 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
   // duplicates per Gaussian: 2.00 vs 1.88 ms) are better served by the 8x4-block kernel.
   const int mode = options().bwd_packed;
   const bool packed = mode == 1 || (mode == 2 && (double)num_entries >= 1.6 * (double)num_gaussians);
+#define GSR_BWD_ARGS(FT, FC)                                                                       \
+  img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas, FT,    \
+      img.n_contrib, FC, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar, acc
   if (variant == kLight) {
-    if (packed)
-      render_bwd2_kernel<kLight><<<grid, kBwd2Threads, 0, stream>>>(
-          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas,
-          nullptr, img.n_contrib, nullptr, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar,
-          acc);
+    if (packed && pose_only)
+      render_bwd2_kernel<kLight, true><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
+    else if (packed)
+      render_bwd2_kernel<kLight, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
+    else if (pose_only)
+      render_bwd_kernel<kLight, true><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
     else
-      render_bwd_kernel<kLight><<<grid, kTileThreads, 0, stream>>>(
-          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas,
-          nullptr, img.n_contrib, nullptr, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar,
-          acc);
+      render_bwd_kernel<kLight, false><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
   } else {
     if (packed)
-      render_bwd2_kernel<kFull><<<grid, kBwd2Threads, 0, stream>>>(
-          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, nullptr,
-          img.final_T, img.n_contrib, img.first_contrib, cot.dL_dpix, cot.dL_ddepth, nullptr,
-          cot.dL_dvar, acc);
+      render_bwd2_kernel<kFull, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
     else
-      render_bwd_kernel<kFull><<<grid, kTileThreads, 0, stream>>>(
-          img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, nullptr,
-          img.final_T, img.n_contrib, img.first_contrib, cot.dL_dpix, cot.dL_ddepth, nullptr,
-          cot.dL_dvar, acc);
+      render_bwd_kernel<kFull, false><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
   }
+#undef GSR_BWD_ARGS
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
 }
