@@ -31,9 +31,10 @@ constexpr int kRedStride = 36;  // floats per slot row in shared memory (144 B: 
 
 // Reduced slot sets: all 14 accumulator slots, or — for -light's tracking mode (map_off: only the
 // pose gradient is wanted) — just the three the pose contraction reads.
-template <bool POSE_ONLY>
+template <int VARIANT, bool POSE_ONLY>
 struct RedSet {
-  static constexpr int N = POSE_ONLY ? 3 : kRedVals;
+  // -full never writes ACC_MED (the last slot), so it reduces one slot less
+  static constexpr int N = POSE_ONLY ? 3 : (VARIANT == kFull ? kRedVals - 1 : kRedVals);
   __device__ static constexpr int slot(int q) {
     return POSE_ONLY ? (q == 0 ? (int)ACC_MX : (q == 1 ? (int)ACC_MY : (int)ACC_PD)) : q;
   }
@@ -43,6 +44,53 @@ __device__ __forceinline__ float fast_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+typedef unsigned long long f2;  // two packed floats (lo = pixel row y0, hi = pixel row y0 + 1)
+
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(f2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float f2_hi(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+// Shared-memory accesses of the warp reduction through precomputed 32-bit shared addresses (kept in
+// two registers across the entry loop, so that no address arithmetic is redone per entry).
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// sum of 16 consecutive floats in shared memory (4 x LDS.128, a packed add tree, one scalar add)
+__device__ __forceinline__ float row16_sum(unsigned addr) {
+  f2 a0, a1, b0, b1, c0, c1, d0, d1;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(addr + 16) : "memory");
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "r"(addr + 32) : "memory");
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d0), "=l"(d1) : "r"(addr + 48) : "memory");
+  const f2 t = f2_add(f2_add(f2_add(a0, a1), f2_add(b0, b1)), f2_add(f2_add(c0, c1), f2_add(d0, d1)));
+  return f2_lo(t) + f2_hi(t);
 }
 
 template <int VARIANT, bool POSE_ONLY>
@@ -107,6 +155,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
   bool mid_once = true;
+  const unsigned red_st = smem_u32(&s_red[warp][lane]);
+  const unsigned red_ld = smem_u32(&s_red[warp][(lane >> 1) * kRedStride + (lane & 1) * 16]);
   const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
 
   for (int i = 0; i < rounds; ++i) {
@@ -233,17 +283,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       }
       // warp reduction through shared memory: every lane stores its column, 28 lanes each add
       // half a row (4 x LDS.128), pairs combine with one shuffle, 14 lanes issue one coalesced red
-      using RS = RedSet<POSE_ONLY>;
-      float* red = s_red[warp];
+      using RS = RedSet<VARIANT, POSE_ONLY>;
 #pragma unroll
-      for (int q = 0; q < RS::N; ++q) red[q * kRedStride + lane] = v[RS::slot(q)];
+      for (int q = 0; q < RS::N; ++q) sts_f32(red_st + q * (kRedStride * 4), v[RS::slot(q)]);
       __syncwarp();
       float sum = 0.f;
       if (lane < 2 * RS::N) {
-        const float4* row = reinterpret_cast<const float4*>(red + (lane >> 1) * kRedStride + (lane & 1) * 16);
-        const float4 a = row[0], b = row[1], c = row[2], d = row[3];
-        sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
-              (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+        sum = row16_sum(red_ld);
       }
       // lane (2q + h) now holds slot q summed over half warp h, i.e. over that half's own entry
       const int j_lo = __shfl_sync(0xffffffffu, j, 0), j_hi = __shfl_sync(0xffffffffu, j, 16);
@@ -273,34 +319,6 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 //  * power / alpha are evaluated with the same rounding sequence as the forward (packed ops are
 //    IEEE round-to-nearest per element), so both passes take identical skip decisions.
 // =================================================================================================
-typedef unsigned long long f2;  // two packed floats (lo = pixel row y0, hi = pixel row y0 + 1)
-
-__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
-  f2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
-  f2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
-  f2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ float f2_lo(f2 v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ float f2_hi(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
-
 constexpr int kBwd2Threads = 128;
 constexpr int kBwd2Warps = kBwd2Threads / 32;
 constexpr int kBwd2Batch = 128;  // entries staged per round (one per thread)
@@ -391,6 +409,8 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   f2 T2 = Tf2;
   f2 Bc0 = 0ull, Bc1 = 0ull, Bc2 = 0ull, Bd = 0ull, Bv = 0ull;  // colour / depth / var "behind" the entry
   bool mid_a = true, mid_b = true;
+  const unsigned red_st = smem_u32(&s_red[warp][lane]);
+  const unsigned red_ld = smem_u32(&s_red[warp][(lane >> 1) * kRedStride + (lane & 1) * 16]);
 
   for (int i = 0; i < rounds; ++i) {
     __syncthreads();
@@ -441,17 +461,12 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       bool vb = (pos < lc_b) && !(pw_b > 0.0f) && !(pw_b < pc);
       if (!__any_sync(0xffffffffu, va || vb)) continue;
       const float o = f2_lo(e2.y);
-      float Ga = 0.f, Gb = 0.f, al_a = 0.f, al_b = 0.f;
-      if (va) {
-        Ga = expf(pw_a);
-        al_a = pair_alpha(o, Ga);
-        va = !(al_a < kAlphaMin);
-      }
-      if (vb) {
-        Gb = expf(pw_b);
-        al_b = pair_alpha(o, Gb);
-        vb = !(al_b < kAlphaMin);
-      }
+      // both exponentials unconditionally (no divergence; a warp that gets here almost always needs
+      // them), results masked afterwards
+      float Ga = expf(pw_a), Gb = expf(pw_b);
+      float al_a = pair_alpha(o, Ga), al_b = pair_alpha(o, Gb);
+      va = va && !(al_a < kAlphaMin);
+      vb = vb && !(al_b < kAlphaMin);
       if (!__any_sync(0xffffffffu, va || vb)) continue;
       if (!va) { Ga = 0.f; al_a = 0.f; }
       if (!vb) { Gb = 0.f; al_b = 0.f; }
@@ -517,18 +532,14 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
         v[ACC_PGY] = f2_mul(q, dy2);
       }
       // warp reduction through shared memory (both pixels of a lane are added first)
-      using RS = RedSet<POSE_ONLY>;
-      float* red = s_red[warp];
+      using RS = RedSet<VARIANT, POSE_ONLY>;
 #pragma unroll
       for (int qn = 0; qn < RS::N; ++qn)
-        red[qn * kRedStride + lane] = f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]);
+        sts_f32(red_st + qn * (kRedStride * 4), f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]));
       __syncwarp();
       float sum = 0.f;
       if (lane < 2 * RS::N) {
-        const float4* row = reinterpret_cast<const float4*>(red + (lane >> 1) * kRedStride + (lane & 1) * 16);
-        const float4 a = row[0], b = row[1], c = row[2], d = row[3];
-        sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) +
-              (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+        sum = row16_sum(red_ld);
       }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       if (lane < 2 * RS::N && (lane & 1) == 0)
