@@ -141,9 +141,14 @@ constexpr int kTileSortCap = 8192;     // entries per tile the shared-memory sor
 constexpr int kTileSortThreads = 256;
 
 // one CTA of 1024 threads; counters[0] = total, counters[2] = longest tile list
+// `capacity` / `longest_cap` (0xFFFFFFFF = unlimited) serve the sync-free "static" binning of the
+// tracker (run_binning_static): ranges are clamped to the buffer and to the longest list the sort
+// was launched for, so that every later kernel stays inside the buffers whatever this frame holds,
+// and counters[3] is raised when something was cut (the host checks it after the fact).
 __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ counters) {
+                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ counters,
+                  uint32_t capacity, uint32_t longest_cap) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry, s_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,7 +180,7 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
     const uint32_t carry = s_carry;
     const uint32_t start = carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
     if (t < tiles) {
-      ranges[t] = make_uint2(start, start + c);
+      ranges[t] = make_uint2(min(start, capacity), min(start + min(c, longest_cap), capacity));
       tile_fill[t] = start;  // scatter cursor
     }
     __syncthreads();
@@ -186,7 +191,11 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
   for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
   if (lane == 0) atomicMax(&s_max, local_max);
   __syncthreads();
-  if (tid == 0) { counters[0] = s_carry; counters[2] = s_max; }
+  if (tid == 0) {
+    counters[0] = s_carry;
+    counters[2] = s_max;
+    if (s_carry > capacity || s_max > longest_cap) counters[3] = 1u;
+  }
 }
 
 // One thread per Gaussian.  tile_fill[t] starts at the tile's range start (scan_tiles_kernel), so
@@ -414,6 +423,31 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
 
 }  // namespace
 
+// Sync-free binning into a caller-owned buffer of `capacity` entries whose longest tile list may
+// not exceed `longest_cap` (tracker: sizes come from a probing frame plus head room).  Nothing is
+// read back; overflow raises g.counters[3] and truncates the frame's lists (memory-safe).
+int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgState& img,
+                       uint32_t capacity, uint32_t longest_cap, cudaStream_t stream) {
+  const int tiles = cam.grid_x * cam.grid_y;
+  if (longest_cap > (uint32_t)kTileSortCap) longest_cap = kTileSortCap;
+  {
+    StageScope st(ST_SCAN, stream, 1);
+    scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
+                                              g.counters, capacity, longest_cap);
+    GSR_LAUNCH_OK(false, stream);
+  }
+  return launch_tile_sort(cam, P, g, img, b, capacity, longest_cap, false, stream);
+}
+
+// Tile scan only (no clamps): leaves the duplicate count in g.counters[0] and the longest tile list
+// in g.counters[2] for the caller to read back.
+int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream_t stream) {
+  scan_tiles_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges,
+                                            img.tile_fill, g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  GSR_LAUNCH_OK(false, stream);
+  return GSR_OK;
+}
+
 int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gsr_alloc_fn alloc,
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
                 cudaStream_t stream) {
@@ -427,7 +461,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
       // img.tile_count was filled by preprocess_fwd (one red per duplicate)
       StageScope st(ST_SCAN, stream, 1);
       scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
-                                                g.counters);
+                                                g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu);
       GSR_LAUNCH_OK(debug, stream);
     }
     // The one host<->device synchronisation of the forward: the duplicate count sizes the binning
@@ -467,7 +501,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
           // estimate too small: reset the scatter cursors (the scan rewrites them) and fall through
           StageScope st(ST_SCAN, stream, 1);
           scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
-                                                    g.counters);
+                                                    g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu);
           GSR_LAUNCH_OK(debug, stream);
         }
       }

@@ -47,6 +47,7 @@ struct Options {
   int tile_sort;
   int bwd_packed;
   int async_binning;
+  int track_headroom_pct;
 };
 Options& options();
 
@@ -431,6 +432,27 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
                             float* out_var, float* gau_unc, int* gau_px, bool debug,
                             cudaStream_t stream);
 
+// Masked L1 loss fused into the -light forward blend (tracker):
+//   L = sum_pix m * (w_color * |C - C_gt|_1 + w_depth * |D - D_gt|),
+//   m = (depth_mask == 0 || D_gt > 0) && (alpha > alpha_thresh)        (mask treated as constant)
+struct FusedLoss {
+  const float* gt_color = nullptr;  // [3,H,W]
+  const float* gt_depth = nullptr;  // [H,W]
+  float w_color = 0.f, w_depth = 0.f, alpha_thresh = -1.f;
+  int depth_mask = 0;
+  float* dL_dpix = nullptr;         // out [3,H,W]
+  float* dL_ddepth = nullptr;       // out [H,W]
+  float* loss_partials = nullptr;   // out [tiles]
+};
+
+int launch_render_fwd_light_loss(const Camera& cam, const GeomState& g, const BinState& b,
+                                 ImgState& img, const float* bg, float* out_color, float* out_depth,
+                                 float* out_median, float* out_alpha, float* out_var,
+                                 const FusedLoss& fl, cudaStream_t stream);
+
+int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgState& img,
+                       uint32_t capacity, uint32_t longest_cap, cudaStream_t stream);
+
 int launch_render_fwd_full(const Camera& cam, const GeomState& g, const BinState& b,
                            ImgState& img, const float* bg, float* out_color, float* out_depth,
                            float* out_unc, bool count_related, bool debug, cudaStream_t stream);
@@ -462,5 +484,12 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
                           const GeomState& g, const float* acc, float* pose_partials,
                           const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
                           cudaStream_t stream);
+
+int preprocess_bwd_blocks(int P);
+int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float* means3D,
+                                   const int* radii, const Camera& cam, const float* perspec,
+                                   const GeomState& g, const float* acc, float* pose_partials,
+                                   cudaStream_t stream);
+int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream_t stream);
 
 }  // namespace gsr

@@ -505,4 +505,24 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   return GSR_OK;
 }
 
+int preprocess_bwd_blocks(int P) { return (P + kBwdThreads - 1) / kBwdThreads; }
+
+// Pose contraction only (tracker): no per-Gaussian gradient is written and the per-block partial
+// sums of the 12 live dL/dviewmatrix entries are left in `pose_partials` for the caller's own
+// reduction (track_update_kernel).
+int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float* means3D,
+                                   const int* radii, const Camera& cam, const float* perspec,
+                                   const GeomState& g, const float* acc, float* pose_partials,
+                                   cudaStream_t stream) {
+  if (variant != kLight) { set_error("pose-only backward exists for -light only"); return GSR_E_INVALID; }
+  const int blocks = preprocess_bwd_blocks(P);
+  StageScope st(ST_PRE_BWD, stream, 1);
+  preprocess_bwd_kernel<kLight, 0><<<blocks, kBwdThreads, 0, stream>>>(
+      P, D, M, means3D, radii, nullptr, g.clamped, nullptr, nullptr, 1.0f, g.cov3D, cam.view, cam.proj,
+      cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc, g.rec, cam.W,
+      cam.H, pose_partials, GaussGradOut{}, false, true);
+  GSR_LAUNCH_OK(false, stream);
+  return GSR_OK;
+}
+
 }  // namespace gsr

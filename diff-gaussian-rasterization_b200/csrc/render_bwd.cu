@@ -143,9 +143,9 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     dLp1 = dL_dpix[1 * HW + pix_id];
     dLp2 = dL_dpix[2 * HW + pix_id];
     dLd = dL_ddepths[pix_id];
-    dLv = dL_dvars[pix_id];
+    dLv = dL_dvars != nullptr ? dL_dvars[pix_id] : 0.f;  // NULL = zero cotangent (tracker)
     gt = gt_depth[pix_id];
-    if (VARIANT == kLight) dLm = dL_dmedians[pix_id];
+    if (VARIANT == kLight && dL_dmedians != nullptr) dLm = dL_dmedians[pix_id];
     if (VARIANT == kFull) first = (int)first_contrib[pix_id];
   }
   float T = T_final;
@@ -387,16 +387,16 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
     Tf_a = (VARIANT == kLight) ? (1 - alphas[pix_a]) : final_Ts[pix_a];
     lc_a = (int)n_contrib[pix_a];
     g0a = dL_dpix[pix_a]; g1a = dL_dpix[HW + pix_a]; g2a = dL_dpix[2 * HW + pix_a];
-    gda = dL_ddepths[pix_a]; gva = dL_dvars[pix_a]; gta = gt_depth[pix_a];
-    if (VARIANT == kLight) gma = dL_dmedians[pix_a];
+    gda = dL_ddepths[pix_a]; gva = dL_dvars != nullptr ? dL_dvars[pix_a] : 0.f; gta = gt_depth[pix_a];
+    if (VARIANT == kLight && dL_dmedians != nullptr) gma = dL_dmedians[pix_a];
     if (VARIANT == kFull) first_a = (int)first_contrib[pix_a];
   }
   if (in_b) {
     Tf_b = (VARIANT == kLight) ? (1 - alphas[pix_b]) : final_Ts[pix_b];
     lc_b = (int)n_contrib[pix_b];
     g0b = dL_dpix[pix_b]; g1b = dL_dpix[HW + pix_b]; g2b = dL_dpix[2 * HW + pix_b];
-    gdb = dL_ddepths[pix_b]; gvb = dL_dvars[pix_b]; gtb = gt_depth[pix_b];
-    if (VARIANT == kLight) gmb = dL_dmedians[pix_b];
+    gdb = dL_ddepths[pix_b]; gvb = dL_dvars != nullptr ? dL_dvars[pix_b] : 0.f; gtb = gt_depth[pix_b];
+    if (VARIANT == kLight && dL_dmedians != nullptr) gmb = dL_dmedians[pix_b];
     if (VARIANT == kFull) first_b = (int)first_contrib[pix_b];
   }
   const f2 Tf2 = f2_pack(Tf_a, Tf_b);

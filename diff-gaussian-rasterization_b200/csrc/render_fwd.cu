@@ -23,7 +23,7 @@ namespace gsr {
 
 namespace {
 
-template <int VARIANT>
+template <int VARIANT, bool LOSS>
 __global__ void __launch_bounds__(kTileThreads)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                   int W, int H, int grid_x, const float4* __restrict__ rec,
@@ -35,7 +35,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   float* __restrict__ gau_unc, int* __restrict__ gau_px,  // light only
                   uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
                   uint32_t* __restrict__ first_contrib, uint32_t* __restrict__ tile_last,
-                  uint32_t* __restrict__ related_counter) {
+                  uint32_t* __restrict__ related_counter, FusedLoss fl) {
   __shared__ float4 s_r0[kTileThreads];
   __shared__ float4 s_r1[kTileThreads];
   __shared__ float4 s_r2[kTileThreads];
@@ -43,6 +43,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ unsigned short s_mask[kTileThreads];                      // sub-block mask per entry
   __shared__ unsigned char s_list[kTileThreads / 16][kTileThreads];    // per-half-warp compacted entries
   __shared__ uint32_t s_red[kTileThreads / 32];
+  __shared__ float s_loss[kTileThreads / 32];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -136,10 +137,12 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         D = GSR_FMA(T, GSR_MUL(alpha, depth), D);
         if (T > 0.5f && test_T < 0.5f) {
           Dmed = depth;
-          const int id = s_id[j];
-          const float dg = GSR_SUB(depth, gt);
-          atomicAdd(gau_unc + id, GSR_MUL(T, GSR_MUL(alpha, GSR_MUL(dg, dg))));
-          atomicAdd(gau_px + id, 1);
+          if (!LOSS) {  // per-Gaussian statistics are not produced by the fused-loss (tracking) pass
+            const int id = s_id[j];
+            const float dg = GSR_SUB(depth, gt);
+            atomicAdd(gau_unc + id, GSR_MUL(T, GSR_MUL(alpha, GSR_MUL(dg, dg))));
+            atomicAdd(gau_px + id, 1);
+          }
         }
         T = test_T;
         last_contributor = contributor;
@@ -160,20 +163,39 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     }
   }
 
+  float my_loss = 0.f;
   if (inside) {
     const size_t HW = (size_t)H * (size_t)W;
     n_contrib[pix_id] = last_contributor;
-    out_color[0 * HW + pix_id] = GSR_FMA(bg[0], T, C0);
-    out_color[1 * HW + pix_id] = GSR_FMA(bg[1], T, C1);
-    out_color[2 * HW + pix_id] = GSR_FMA(bg[2], T, C2);
-    out_depth[pix_id] = D;
+    const float c0 = GSR_FMA(bg[0], T, C0), c1 = GSR_FMA(bg[1], T, C1), c2 = GSR_FMA(bg[2], T, C2);
+    if (!LOSS || out_color != nullptr) {
+      out_color[0 * HW + pix_id] = c0;
+      out_color[1 * HW + pix_id] = c1;
+      out_color[2 * HW + pix_id] = c2;
+      out_depth[pix_id] = D;
+    }
     out_aux0[pix_id] = Wsum;
     if (VARIANT == kLight) {
-      out_median[pix_id] = Dmed;
-      out_var[pix_id] = 0.0f;  // the reference never updates D_var (light forward.cu:317,410)
+      if (!LOSS || out_median != nullptr) {
+        out_median[pix_id] = Dmed;
+        out_var[pix_id] = 0.0f;  // the reference never updates D_var (light forward.cu:317,410)
+      }
     } else {
       final_T[pix_id] = T;
       first_contrib[pix_id] = first;
+    }
+    if (LOSS) {
+      // fused masked-L1 loss and its cotangents (tracker.cu): the images need not leave the chip
+      const float gtd = fl.gt_depth[pix_id];
+      const bool m = (fl.depth_mask == 0 || gtd > 0.0f) && (Wsum > fl.alpha_thresh);
+      const float wc = m ? fl.w_color : 0.f, wd = m ? fl.w_depth : 0.f;
+      const float e0 = c0 - fl.gt_color[0 * HW + pix_id], e1 = c1 - fl.gt_color[1 * HW + pix_id],
+                  e2 = c2 - fl.gt_color[2 * HW + pix_id], ed = D - gtd;
+      fl.dL_dpix[0 * HW + pix_id] = e0 > 0.f ? wc : (e0 < 0.f ? -wc : 0.f);
+      fl.dL_dpix[1 * HW + pix_id] = e1 > 0.f ? wc : (e1 < 0.f ? -wc : 0.f);
+      fl.dL_dpix[2 * HW + pix_id] = e2 > 0.f ? wc : (e2 < 0.f ? -wc : 0.f);
+      fl.dL_ddepth[pix_id] = ed > 0.f ? wd : (ed < 0.f ? -wd : 0.f);
+      my_loss = wc * ((fabsf(e0) + fabsf(e1)) + fabsf(e2)) + wd * fabsf(ed);
     }
   }
 
@@ -185,9 +207,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   for (int o = 16; o > 0; o >>= 1) {
     m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (LOSS) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
   }
   __syncthreads();
   if (lane == 0) s_red[warp] = m;
+  if (LOSS && lane == 0) s_loss[warp] = my_loss;
   if (VARIANT == kFull && related_counter != nullptr && lane == 0 && v != 0)
     atomicAdd(related_counter, v);
   __syncthreads();
@@ -196,6 +220,12 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 #pragma unroll
     for (int k = 0; k < kTileThreads / 32; ++k) mm = max(mm, s_red[k]);
     tile_last[tile] = mm;
+    if (LOSS) {  // fixed summation order: the loss value is deterministic
+      float l = 0.f;
+#pragma unroll
+      for (int k = 0; k < kTileThreads / 32; ++k) l += s_loss[k];
+      fl.loss_partials[tile] = l;
+    }
   }
 }
 
@@ -208,11 +238,28 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
                             cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
-  render_fwd_kernel<kLight><<<grid, kTileThreads, 0, stream>>>(
+  render_fwd_kernel<kLight, false><<<grid, kTileThreads, 0, stream>>>(
       img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, out_color, out_depth,
       out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
-      img.tile_last, nullptr);
+      img.tile_last, nullptr, FusedLoss{});
   GSR_LAUNCH_OK(debug, stream);
+  return GSR_OK;
+}
+
+// -light forward blend with the masked-L1 loss and its cotangents fused into the epilogue
+// (tracker.cu).  Only alpha, n_contrib, tile_last, the cotangent images and the per-tile loss
+// partials are written; out_color / out_depth / out_median / out_var may be NULL.
+int launch_render_fwd_light_loss(const Camera& cam, const GeomState& g, const BinState& b,
+                                 ImgState& img, const float* bg, float* out_color, float* out_depth,
+                                 float* out_median, float* out_alpha, float* out_var,
+                                 const FusedLoss& fl, cudaStream_t stream) {
+  dim3 grid(cam.grid_x, cam.grid_y, 1);
+  StageScope st(ST_RENDER_FWD, stream);
+  render_fwd_kernel<kLight, true><<<grid, kTileThreads, 0, stream>>>(
+      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, fl.gt_depth, out_color, out_depth,
+      out_alpha, out_median, out_var, nullptr, nullptr, img.n_contrib, nullptr, nullptr,
+      img.tile_last, nullptr, fl);
+  GSR_LAUNCH_OK(false, stream);
   return GSR_OK;
 }
 
@@ -221,10 +268,10 @@ int launch_render_fwd_full(const Camera& cam, const GeomState& g, const BinState
                            float* out_unc, bool count_related, bool debug, cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
-  render_fwd_kernel<kFull><<<grid, kTileThreads, 0, stream>>>(
+  render_fwd_kernel<kFull, false><<<grid, kTileThreads, 0, stream>>>(
       img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, nullptr, out_color, out_depth,
       out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,
-      img.tile_last, count_related ? (g.counters + 1) : nullptr);
+      img.tile_last, count_related ? (g.counters + 1) : nullptr, FusedLoss{});
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
 }

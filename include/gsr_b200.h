@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_B200_ABI_VERSION 2
+#define GSR_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GSR_API __attribute__((visibility("default")))
@@ -89,6 +89,9 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   the host has read this frame's count, so the GPU does not idle during the
  *                   read-back (guarded kernels; the binning is redone when the estimate was too
  *                   small); 0: wait for the count first, exact buffer size.
+ *   "track_headroom_pct" head room (percent, default 50) of the tracker's binning buffer over the
+ *                   counts of its probing forward; negative values force the overflow / retry path
+ *                   (test hook).
  * Returns the previous value, or GSR_E_INVALID for an unknown key. */
 GSR_API int gsr_set_option(const char* key, int value);
 GSR_API int gsr_get_option(const char* key);
@@ -207,6 +210,61 @@ GSR_API int gsr_sh_grad_from_views(int P, int D, int M, const float* means3D, in
                                    const float* dR_all, size_t view_stride,
                                    const float* campos_all, size_t campos_stride,
                                    float* dL_dsh, void* stream);
+
+/* ---- pose tracker (not part of the reference surface) ------------
+ * K iterations of CG-SLAM's tracking loop — render(-light, map_off) -> masked L1 colour + depth loss
+ * -> backward -> dL/dviewmatrix -> chain rule to (quaternion, translation) -> Adam step — run on the
+ * device with no host interaction: one iteration is 8 kernels + 1 memset captured in a CUDA graph
+ * (static-capacity binning, loss and cotangents fused into the forward blend, pose update on chip).
+ * It replaces, for this loop, the reference's per-iteration sequence
+ *   _C.rasterize_gaussians (L/rasterize_points.cu:36-128, blocking count read-back
+ *   L/cuda_rasterizer/rasterizer_impl.cu:287) -> torch loss -> _C.rasterize_gaussians_backward
+ *   (L/rasterize_points.cu:130-235) -> torch.sum(dL_dview) (L/diff_gaussian_rasterization/__init__.py:160)
+ *   -> autograd through the pose parametrisation -> torch.optim.Adam.
+ * Pose: W2C = [R(q/|q|) t; 0 1], q = (w,x,y,z); viewmatrix = W2C^T in the reference's layout.
+ * Loss: L = sum_pix m (w_color |C - C_gt|_1 + w_depth |D - D_gt|),
+ *       m = (use_depth_mask == 0 || D_gt > 0) && (alpha > alpha_thresh), mask treated as constant. */
+typedef struct gsr_tracker gsr_tracker;
+
+typedef struct gsr_track_params {
+  float w_color, w_depth;   /* loss weights */
+  float alpha_thresh;       /* silhouette mask threshold on the rendered alpha; < 0: off */
+  int use_depth_mask;       /* 1: only pixels with gt_depth > 0 */
+  float lr_rot, lr_trans;   /* Adam learning rates of the quaternion / the translation */
+  float beta1, beta2, eps;  /* Adam constants (torch.optim.Adam semantics) */
+} gsr_track_params;
+
+typedef struct gsr_track_result {
+  float q[4], t[3];            /* pose after the last iteration */
+  float last_dL_dview[16];     /* dL/dviewmatrix of the last iteration (reference layout, before the step) */
+  float last_grad[7];          /* dL/dq[4], dL/dt[3] of the last iteration */
+  int iterations;              /* iterations run */
+  int num_rendered;            /* (Gaussian, tile) duplicates of the probing forward at the start pose */
+  int retries;                 /* reruns after a binning-buffer overflow */
+  int kernels_per_iteration;   /* graph nodes per iteration */
+} gsr_track_result;
+
+/* perspec_matrix_host: 16 floats on the HOST, the reference's `perspec_matrix` argument (P^T row-major).
+ * max_iterations bounds `iterations` of gsr_tracker_run (size of the device-side loss history).
+ * Returns NULL on failure (see gsr_last_error). */
+GSR_API gsr_tracker* gsr_tracker_create(int P, int D, int M, int width, int height, float tan_fovx,
+                                        float tan_fovy, const float* perspec_matrix_host,
+                                        int max_iterations);
+GSR_API void gsr_tracker_destroy(gsr_tracker* t);
+/* Device pointers, borrowed (must stay valid and unchanged in address while the tracker uses them);
+ * same meaning and optional-NULL rules as gsr_light_forward. */
+GSR_API int gsr_tracker_set_scene(gsr_tracker* t, const float* means3D, const float* shs,
+                                  const float* colors_precomp, const float* opacities,
+                                  const float* scales, float scale_modifier, const float* rotations,
+                                  const float* cov3D_precomp, const float* background);
+/* gt_color[3,H,W], gt_depth[H,W]: device pointers, borrowed. */
+GSR_API int gsr_tracker_set_frame(gsr_tracker* t, const float* gt_color, const float* gt_depth);
+/* Host pointers; resets the Adam state. */
+GSR_API int gsr_tracker_set_pose(gsr_tracker* t, const float* quat_wxyz, const float* trans);
+/* Runs `iterations` tracking iterations from the current pose (Adam state carries over between
+ * calls) and blocks until they are done.  loss_history (host, [iterations]) and result may be NULL. */
+GSR_API int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iterations,
+                            float* loss_history, gsr_track_result* result);
 
 /* replaces Rasterizer::markVisible (rasterizer.h:24-29): present[i] = view-space z > 0.2.
  * `present` is one byte per Gaussian (0/1). */

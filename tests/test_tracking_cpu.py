@@ -1,0 +1,105 @@
+"""CPU tests of the tracker's host-side pieces: the pose oracle (oracle/pose_oracle.py) pinned
+against torch autograd + torch.optim.Adam, the torch tracking-loop helpers, and the C-ABI exports."""
+import ctypes
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+po = _load("pose_oracle", os.path.join(ROOT, "oracle", "pose_oracle.py"))
+trk = _load("gsr_b200_tracking", os.path.join(ge.PKG, "tracking.py"))
+
+
+def _random_pose(seed):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4)
+    q = q / np.linalg.norm(q) * rng.uniform(0.7, 1.4)  # deliberately not unit length
+    return q, rng.normal(size=3)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_pose_gradient_matches_autograd(seed):
+    q0, t0 = _random_pose(seed)
+    rng = np.random.default_rng(100 + seed)
+    dview = rng.normal(size=(4, 4))
+    dview[:, 3] = 0.0  # entries 3, 7, 11, 15 are always zero in the reference's dL_dview
+    q = torch.tensor(q0, dtype=torch.float64, requires_grad=True)
+    t = torch.tensor(t0, dtype=torch.float64, requires_grad=True)
+    R = trk.quat_to_rotation(q)
+    w2c = torch.cat([torch.cat([R, t[:, None]], dim=1),
+                     torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float64)], dim=0)
+    (w2c.t() * torch.tensor(dview)).sum().backward()
+    gq, gt = po.pose_gradient(q0, dview.reshape(-1))
+    np.testing.assert_allclose(gq, q.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(gt, t.grad.numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_adam_matches_torch():
+    rng = np.random.default_rng(7)
+    p0 = rng.normal(size=7)
+    q = torch.tensor(p0[:4], dtype=torch.float64, requires_grad=True)
+    t = torch.tensor(p0[4:], dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([{"params": [q], "lr": 4e-4}, {"params": [t], "lr": 2e-3}],
+                           betas=(0.9, 0.999), eps=1e-8)
+    ad = po.Adam(4e-4, 2e-3)
+    p = p0.copy()
+    for k in range(25):
+        g = rng.normal(size=7) * (10.0 ** rng.integers(-3, 3))
+        q.grad = torch.tensor(g[:4])
+        t.grad = torch.tensor(g[4:])
+        opt.step()
+        p = ad.step(p, g)
+        np.testing.assert_allclose(p, np.concatenate([q.detach().numpy(), t.detach().numpy()]),
+                                   rtol=1e-9, atol=1e-12)
+
+
+def test_camera_from_pose_matches_scene_generator():
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(64, 48)
+    q = trk.rotation_to_quat(cam.w2c[:3, :3])
+    view, proj, campos = po.camera_from_pose(q.numpy(), cam.w2c[:3, 3].numpy(), cam.perspec_matrix.numpy())
+    np.testing.assert_allclose(view, cam.viewmatrix.numpy(), atol=2e-6)
+    np.testing.assert_allclose(proj, cam.projmatrix.numpy(), atol=2e-5)
+    np.testing.assert_allclose(campos, cam.campos.numpy(), atol=2e-6)
+    np.testing.assert_allclose(po.quat_to_R(q.numpy()), trk.quat_to_rotation(q.double()).numpy(), atol=1e-7)
+
+
+def test_masked_l1_matches_autograd():
+    rng = np.random.default_rng(3)
+    H, W = 12, 20
+    color = torch.tensor(rng.uniform(0, 1, size=(3, H, W)), requires_grad=True)
+    depth = torch.tensor(rng.uniform(0.5, 5, size=(H, W)), requires_grad=True)
+    alpha = rng.uniform(0.9, 1.0, size=(H, W))
+    gtc = rng.uniform(0, 1, size=(3, H, W))
+    gtd = rng.uniform(0.5, 5, size=(H, W)) * (rng.uniform(size=(H, W)) > 0.2)
+    mask = torch.tensor(((alpha > 0.95) & (gtd > 0)).astype(np.float64))
+    loss = 0.5 * (mask * (color - torch.tensor(gtc)).abs()).sum() + 1.0 * (mask * (depth - torch.tensor(gtd)).abs()).sum()
+    loss.backward()
+    l, dc, dd = po.masked_l1(color.detach().numpy(), depth.detach().numpy(), alpha, gtc, gtd, 0.5, 1.0, 0.95, True)
+    assert abs(l - float(loss)) < 1e-9
+    np.testing.assert_allclose(dc, color.grad.numpy())
+    np.testing.assert_allclose(dd, depth.grad.numpy())
+
+
+def test_tracker_symbols_exported():
+    lib = ctypes.CDLL(ge.core_library_path())
+    for name in ("gsr_tracker_create", "gsr_tracker_destroy", "gsr_tracker_set_scene",
+                 "gsr_tracker_set_frame", "gsr_tracker_set_pose", "gsr_tracker_run"):
+        assert hasattr(lib, name), name
+    assert ctypes.sizeof(trk.TrackParams) == 36
+    assert ctypes.sizeof(trk.TrackResult) == 4 * (4 + 3 + 16 + 7 + 4)

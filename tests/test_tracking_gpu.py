@@ -1,0 +1,184 @@
+"""GPU tests of the device-side pose tracker (csrc/tracker.cu).
+
+The tracker is compared with the same loop written through the public -light surface
+(tracking.torch_tracking_loop: GaussianRasterizer + torch loss + autograd through the pose
+parametrisation + torch.optim.Adam), with the numpy pose oracle, and — when baseline/_ref is on the
+box — with the loop driven by the reference's own CUDA build.  Tolerances: loss 1e-4 relative,
+pose gradient 1e-3 relative (the north star's gradient tolerance), poses 1e-4 absolute.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import parity_util as pu
+
+ge = pu.ge
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup(P=4000, W=192, H=128, sig=(2.0, 10.0), seed=5, use_sh=True):
+    """A scene, the frame rendered at the true pose (ground truth), and a perturbed start pose."""
+    sc = ge.load_scene_module()
+    trk = ge.load_tracking_module()
+    cam = sc.make_camera(W, H)
+    scene = sc.make_scene(P, cam, sig, seed=seed, backdrop=True)
+    d = lambda t: t.to(DEV).contiguous()
+    S = dict(means3D=d(scene.means3D), opacities=d(scene.opacities), scales=d(scene.scales),
+             rotations=d(scene.rotations), shs=d(scene.shs), colors=d(scene.colors), bg=d(scene.bg))
+    mod = ge.load_variant("light")
+    rs = pu.settings_for(mod, "light", cam, scene, DEV, 3, False, True)
+    with torch.no_grad():
+        res = mod.GaussianRasterizer(rs)(
+            means3D=S["means3D"], means2D=torch.zeros_like(S["means3D"]), opacities=S["opacities"],
+            shs=S["shs"] if use_sh else None, colors_precomp=None if use_sh else S["colors"],
+            scales=S["scales"], rotations=S["rotations"], cov3D_precomp=None,
+            viewmatrix=d(cam.viewmatrix), gt_depth=d(scene.gt_depth))
+    gt_color, gt_depth = res[0].contiguous(), res[2][0].contiguous()
+    q_true = trk.rotation_to_quat(cam.w2c[:3, :3])
+    t_true = cam.w2c[:3, 3].clone()
+    # start pose: 0.6 degrees off about (0.3, -1, 0.5), 1.5 cm off in translation
+    ax = torch.tensor([0.3, -1.0, 0.5], dtype=torch.float64)
+    ax = ax / ax.norm()
+    th = math.radians(0.6)
+    dq = torch.tensor([math.cos(th / 2), *(math.sin(th / 2) * ax).tolist()], dtype=torch.float64)
+    w1, x1, y1, z1 = dq.tolist()
+    w2, x2, y2, z2 = q_true.double().tolist()
+    q0 = [w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+          w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2]
+    t0 = (t_true + torch.tensor([0.010, -0.008, 0.007])).tolist()
+    return dict(trk=trk, cam=cam, scene=S, gt_color=gt_color, gt_depth=gt_depth, q_true=q_true.tolist(),
+                t_true=t_true.tolist(), q0=q0, t0=t0, P=P, W=W, H=H, use_sh=use_sh, mod=mod)
+
+
+def _tracker(s, max_iterations=128):
+    trk, cam, S = s["trk"], s["cam"], s["scene"]
+    t = trk.PoseTracker(s["P"], 3, 16, s["H"], s["W"], cam.tanfovx, cam.tanfovy, cam.perspec_matrix,
+                        max_iterations=max_iterations)
+    t.set_scene(S["means3D"], S["opacities"], shs=S["shs"] if s["use_sh"] else None,
+                colors_precomp=None if s["use_sh"] else S["colors"], scales=S["scales"],
+                rotations=S["rotations"], bg=S["bg"])
+    t.set_frame(s["gt_color"], s["gt_depth"])
+    t.set_pose(s["q0"], s["t0"])
+    return t
+
+
+def _loop(s, mod, iters, **prm):
+    cam = s["cam"]
+    return s["trk"].torch_tracking_loop(mod, s["scene"], s["gt_color"], s["gt_depth"], s["H"], s["W"],
+                                        cam.tanfovx, cam.tanfovy, cam.perspec_matrix, s["q0"], s["t0"],
+                                        iters, sh_degree=3, use_sh=s["use_sh"], **prm)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _pose_err(q, t, s):
+    po = ge.load_pose_oracle()
+    R, Rt = po.quat_to_R(q), po.quat_to_R(s["q_true"])
+    ang = math.degrees(math.acos(max(-1.0, min(1.0, (np.trace(R.T @ Rt) - 1) / 2))))
+    return ang, float(np.linalg.norm(np.asarray(t) - np.asarray(s["t_true"])))
+
+
+@pytest.mark.parametrize("use_sh", [True, False])
+def test_first_iteration_matches_torch_loop_and_oracle(built, use_sh):
+    s = _setup(use_sh=use_sh)
+    trk = _tracker(s)
+    prm = dict(alpha_thresh=0.5)
+    got = trk.run(1, **prm)
+    ref = _loop(s, s["mod"], 1, **prm)
+    assert got["retries"] == 0 and got["num_rendered"] > 0
+    assert abs(got["loss"][0] - ref["loss"][0]) <= 1e-4 * abs(ref["loss"][0])
+    assert _rel(got["last_dL_dview"], ref["dL_dview"][0].numpy()) <= pu.GRAD_RTOL
+    assert _rel(got["last_grad"], ref["grads"][0].numpy()) <= pu.GRAD_RTOL
+    # chain rule + Adam step against the numpy oracle, fed with the tracker's own dL_dview
+    po = ge.load_pose_oracle()
+    gq, gt = po.pose_gradient(s["q0"], got["last_dL_dview"])
+    assert _rel(got["last_grad"], np.concatenate([gq, gt])) <= 1e-5
+    p1 = po.Adam(4e-4, 2e-3).step(np.array(s["q0"] + s["t0"], dtype=np.float64), np.concatenate([gq, gt]))
+    np.testing.assert_allclose(got["q"] + got["t"], p1, atol=2e-6)
+    trk.close()
+
+
+def test_iterations_match_torch_loop(built):
+    s = _setup()
+    trk = _tracker(s)
+    K = 12
+    got = trk.run(K)
+    ref = _loop(s, s["mod"], K)
+    for k in range(K):
+        assert abs(got["loss"][k] - ref["loss"][k]) <= 2e-3 * abs(ref["loss"][k]), (k, got["loss"][k], ref["loss"][k])
+    np.testing.assert_allclose(got["q"], ref["q"], atol=1e-4)
+    np.testing.assert_allclose(got["t"], ref["t"], atol=1e-4)
+    trk.close()
+
+
+def test_tracker_converges_to_the_true_pose(built):
+    s = _setup()
+    trk = _tracker(s)
+    a0, d0 = _pose_err(s["q0"], s["t0"], s)
+    got = trk.run(100, alpha_thresh=0.5)
+    a1, d1 = _pose_err(got["q"], got["t"], s)
+    assert got["loss"][-1] < 0.35 * got["loss"][0], (got["loss"][0], got["loss"][-1])
+    assert a1 < 0.4 * a0 and d1 < 0.4 * d0, (a0, d0, a1, d1)
+    # a second call continues from the current pose and Adam state
+    more = trk.run(20, alpha_thresh=0.5)
+    assert more["loss"][0] <= 1.5 * got["loss"][-1]
+    trk.close()
+
+
+def test_tracker_is_reproducible_and_restartable(built):
+    s = _setup(P=2500, W=128, H=96)
+    a = _tracker(s)
+    r1 = a.run(8)
+    a.set_pose(s["q0"], s["t0"])
+    r2 = a.run(8)
+    # same up to the summation order of the backward's floating-point atomics
+    np.testing.assert_allclose(r1["loss"], r2["loss"], rtol=1e-4)
+    np.testing.assert_allclose(r1["q"] + r1["t"], r2["q"] + r2["t"], atol=2e-5)
+    a.close()
+
+
+def test_binning_overflow_is_detected_and_retried(built):
+    s = _setup(P=3000, W=160, H=96)
+    want = _tracker(s).run(5)
+    old = pu.set_option("track_headroom_pct", -80)
+    try:
+        trk = _tracker(s)
+        got = trk.run(5)
+    finally:
+        pu.set_option("track_headroom_pct", old)
+    assert got["retries"] >= 1
+    np.testing.assert_allclose(got["loss"], want["loss"], rtol=1e-4)
+    np.testing.assert_allclose(got["q"] + got["t"], want["q"] + want["t"], atol=2e-5)
+    trk.close()
+
+
+def test_matches_loop_through_the_reference_build(built):
+    ref_mod = built.load_reference("light")
+    if ref_mod is None:
+        pytest.skip("baseline/_ref not present on this box")
+    s = _setup()
+    trk = _tracker(s)
+    got = trk.run(6)
+    ref = _loop(s, ref_mod, 6)
+    assert abs(got["loss"][0] - ref["loss"][0]) <= 1e-4 * abs(ref["loss"][0])
+    for k in range(6):
+        assert abs(got["loss"][k] - ref["loss"][k]) <= 2e-3 * abs(ref["loss"][k]), (k, got["loss"][k], ref["loss"][k])
+    np.testing.assert_allclose(got["q"], ref["q"], atol=1e-4)
+    np.testing.assert_allclose(got["t"], ref["t"], atol=1e-4)
+    trk.close()
+
+
+def test_bad_arguments_are_rejected(built):
+    s = _setup(P=500, W=64, H=48)
+    trk = _tracker(s, max_iterations=4)
+    with pytest.raises(RuntimeError):
+        trk.run(5)  # more than max_iterations
+    with pytest.raises(ValueError):
+        trk.set_frame(s["gt_color"].cpu(), s["gt_depth"])
+    trk.close()
