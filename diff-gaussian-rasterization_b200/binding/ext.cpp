@@ -11,4 +11,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // extension (not in the reference): flat scene-gradient arena for view-level data parallelism
   m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false);
   m.def("sh_grad_from_views", &shGradFromViews);
+  // extension (not in the reference): in-kernel densification statistics
+  m.def("set_densify_stats", &setDensifyStats, pybind11::arg("grad_accum"), pybind11::arg("denom"),
+        pybind11::arg("max_radii2D"));
 }

@@ -48,6 +48,7 @@ torch::Tensor scratch_for(int P, const torch::TensorOptions& fopts) {
 }
 
 torch::Tensor g_grad_arena;  // see setGradArena
+torch::Tensor g_densify_accum, g_densify_denom, g_max_radii;  // see setDensifyStats
 bool g_arena_factorized = false;
 
 struct SceneGrads {
@@ -55,6 +56,16 @@ struct SceneGrads {
   torch::Tensor masked_color;  // factorized arena only
   bool factorized = false;
 };
+
+// densification accumulators registered with setDensifyStats, when they fit this scene
+void fill_densify(gsr_backward_extras& ex, int P, const torch::Tensor& like) {
+  if (g_densify_accum.defined() && g_densify_accum.numel() == P && g_densify_accum.device() == like.device()) {
+    ex.densify_grad_accum = g_densify_accum.data_ptr<float>();
+    ex.densify_denom = g_densify_denom.data_ptr<float>();
+  }
+  if (g_max_radii.defined() && g_max_radii.numel() == P && g_max_radii.device() == like.device())
+    ex.max_radii2D = g_max_radii.data_ptr<float>();
+}
 
 // the five scene-parameter gradients: views of the registered arena when it fits, fresh tensors otherwise
 SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torch::TensorOptions& fopts) {
@@ -201,7 +212,8 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
-  gsr_backward_extras extras{nullptr, 0};
+  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr};
+  fill_densify(extras, P, means3D);
   if (sg.factorized) {
     extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
     extras.skip_sh_grad = 1;
@@ -327,7 +339,8 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
-  gsr_backward_extras extras{nullptr, 0};
+  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr};
+  fill_densify(extras, P, means3D);
   if (sg.factorized) {
     extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
     extras.skip_sh_grad = 1;
@@ -367,6 +380,30 @@ RasterizeGaussiansBackwardCUDA(
 }
 
 #endif
+
+// Registers (or, with undefined / empty tensors, clears) the densification accumulators that the
+// following backward calls update in place (gsr_backward_extras in include/gsr_b200.h).
+void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom,
+                     const torch::Tensor& max_radii2D) {
+  auto ok = [](const torch::Tensor& t) {
+    return t.defined() && t.numel() > 0;
+  };
+  auto check = [](const torch::Tensor& t, const char* name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.is_contiguous(), name,
+                " must be a contiguous float32 CUDA tensor");
+  };
+  g_densify_accum = torch::Tensor(); g_densify_denom = torch::Tensor(); g_max_radii = torch::Tensor();
+  if (ok(grad_accum) || ok(denom)) {
+    TORCH_CHECK(ok(grad_accum) && ok(denom) && grad_accum.numel() == denom.numel(),
+                "grad_accum and denom must be given together and have the same number of elements");
+    check(grad_accum, "grad_accum"); check(denom, "denom");
+    g_densify_accum = grad_accum; g_densify_denom = denom;
+  }
+  if (ok(max_radii2D)) {
+    check(max_radii2D, "max_radii2D");
+    g_max_radii = max_radii2D;
+  }
+}
 
 void setGradArena(const torch::Tensor& arena, bool factorized_sh) {
   g_arena_factorized = factorized_sh;

@@ -80,6 +80,8 @@ RasterizeGaussiansBackwardCUDA(
 // instead of dL_dsh (whose returned tensor is undefined / None); the summed dL_dsh of all views is
 // rebuilt with shGradFromViews after an all-gather of the first 3P + 4 floats.
 void setGradArena(const torch::Tensor& arena, bool factorized_sh);
+void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom,
+                     const torch::Tensor& max_radii2D);
 
 // gathered: [nviews, 3P + 4] (rows = the first 3P + 4 floats of each rank's factorized arena).
 // Returns sum over views of dL_dsh, [P, M, 3].

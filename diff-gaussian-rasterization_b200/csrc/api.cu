@@ -387,10 +387,15 @@ int gsr_light_backward(
     if (rc != GSR_OK) return rc;
   }
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
-                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr};
+                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr};
   if (extras != nullptr) {
     out.dL_dcolor_masked = extras->dL_dcolor_masked;
     if (extras->skip_sh_grad) out.dL_dsh = nullptr;
+    if (extras->densify_grad_accum != nullptr && extras->densify_denom != nullptr) {
+      out.densify_grad_accum = extras->densify_grad_accum;
+      out.densify_denom = extras->densify_denom;
+    }
+    out.max_radii2D = extras->max_radii2D;
   }
   return launch_preprocess_bwd(kLight, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
@@ -435,10 +440,15 @@ int gsr_full_backward(
   rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, false, s);
   if (rc != GSR_OK) return rc;
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
-                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr};
+                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr};
   if (extras != nullptr) {
     out.dL_dcolor_masked = extras->dL_dcolor_masked;
     if (extras->skip_sh_grad) out.dL_dsh = nullptr;
+    if (extras->densify_grad_accum != nullptr && extras->densify_denom != nullptr) {
+      out.densify_grad_accum = extras->densify_grad_accum;
+      out.densify_denom = extras->densify_denom;
+    }
+    out.max_radii2D = extras->max_radii2D;
   }
   return launch_preprocess_bwd(kFull, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,

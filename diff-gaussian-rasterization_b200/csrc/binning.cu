@@ -230,10 +230,18 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
     const uint32_t x0 = rx & 0xFFFFu, x1 = rx >> 16, y0 = ry & 0xFFFFu, y1 = ry >> 16;
     const uint32_t w = x1 - x0, total = w * (y1 - y0);
     const uint64_t e = ((uint64_t)e_hi << 32) | e_lo;
-    for (uint32_t q = lane; q < total; q += 32) {
-      const uint32_t t = (y0 + q / w) * (uint32_t)grid_x + x0 + q % w;
-      const uint32_t slot = atomicAdd(tile_fill + t, 1u);
-      if (slot < capacity) entries[slot] = e;
+    // four atomics in flight per lane before the dependent stores (a wide splat is otherwise a
+    // chain of atomic round trips)
+    for (uint32_t q0 = lane; q0 < total; q0 += 128) {
+      uint32_t slot[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u) {
+        const uint32_t q = q0 + 32u * u;
+        if (q < total) slot[u] = atomicAdd(tile_fill + (y0 + q / w) * (uint32_t)grid_x + x0 + q % w, 1u);
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u)
+        if (q0 + 32u * u < total && slot[u] < capacity) entries[slot[u]] = e;
     }
   }
   if (n != 0u && n <= kWide) {

@@ -475,6 +475,9 @@ struct GaussGradOut {
   float* dL_dmean3D; float* dL_dcov3D; float* dL_dsh; float* dL_dscale; float* dL_drot;
   float* dL_dview;
   float* dL_dcolor_masked;  // optional [P,3]: dL/dcolor with clamped channels zeroed (see gsr_backward_extras)
+  float* densify_grad_accum;  // optional in/out [P]: += |dL/dmean2D.xy| for visible Gaussians
+  float* densify_denom;       // optional in/out [P]: += 1 for visible Gaussians
+  float* max_radii2D;         // optional in/out [P]: max(., radius) for visible Gaussians
 };
 
 int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D,
@@ -488,8 +491,8 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
 int preprocess_bwd_blocks(int P);
 int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float* means3D,
                                    const int* radii, const Camera& cam, const float* perspec,
-                                   const GeomState& g, const float* acc, float* pose_partials,
-                                   cudaStream_t stream);
+                                   const GeomState& g, float* acc, float* pose_partials,
+                                   bool clear_acc, cudaStream_t stream);
 int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream_t stream);
 
 }  // namespace gsr

@@ -48,7 +48,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ perspec, float fx, float fy, float tanx, float tany,
                       const float* __restrict__ acc, const float4* __restrict__ g_rec, int img_w,
                       int img_h, float* __restrict__ pose_partials, GaussGradOut out,
-                      bool want_gauss, bool want_pose) {
+                      bool want_gauss, bool want_pose, float* __restrict__ acc_clear) {
   extern __shared__ float sh_smem[];  // [kBwdThreads][M*3+1] SH in, dL/dSH out
   __shared__ float s_pose[kBwdThreads / 32][12];
   const int base = blockIdx.x * kBwdThreads;
@@ -96,6 +96,11 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   if (live) {
     const float4* a4 = reinterpret_cast<const float4*>(acc + (size_t)idx * kAccStride);
     const float4 a0 = a4[0], a1 = a4[1], a2 = a4[2], a3 = a4[3];
+    if (acc_clear != nullptr) {  // tracker: leave the line zeroed for the next iteration (no memset pass)
+      float4* z4 = reinterpret_cast<float4*>(acc_clear + (size_t)idx * kAccStride);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      z4[0] = z; z4[1] = z; z4[2] = z; z4[3] = z;
+    }
     // moments of w = G dL/dalpha (render_bwd) -> screen-space gradients with this Gaussian's conic:
     //   dL/dmean2D.x = 0.5 W o (-A S1 - B S2),  dL/dconic = -0.5 o (S11, S12, S22),  dL/dopacity = S0
     const float4 rec0 = g_rec[3 * (size_t)idx + 0], rec1 = g_rec[3 * (size_t)idx + 1];
@@ -368,6 +373,14 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 
       st3(out.dL_dmean3D, idx, dmean.x, dmean.y, dmean.z);
       st3(out.dL_dmean2D, idx, g_mx, g_my, 0.f);
+      // densification statistics of Inria 3DGS / CG-SLAM mapping (add_densification_stats:
+      // xyz_gradient_accum += |viewspace grad.xy|, denom += 1, max_radii2D = max(., radii) over the
+      // visible Gaussians), accumulated here instead of by five torch kernels over [P]
+      if (out.densify_grad_accum != nullptr) {
+        out.densify_grad_accum[idx] += sqrtf(g_mx * g_mx + g_my * g_my);
+        out.densify_denom[idx] += 1.0f;
+      }
+      if (out.max_radii2D != nullptr) out.max_radii2D[idx] = fmaxf(out.max_radii2D[idx], (float)radii[idx]);
       if (out.dL_dconic) reinterpret_cast<float4*>(out.dL_dconic)[idx] = make_float4(g_ca, g_cb, 0.f, g_cc);
       if (out.dL_dopacity) out.dL_dopacity[idx] = g_op;
       st3(out.dL_dcolor, idx, g_r, g_g, g_b);
@@ -482,7 +495,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   preprocess_bwd_kernel<V, MT><<<blocks, kBwdThreads, smem, stream>>>(                           \
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
-      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose)
+      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr)
 #define GSR_PRE_BWD_M(V)                                                                         \
   switch (M) {                                                                                   \
     case 16: GSR_PRE_BWD(V, 16); break;                                                          \
@@ -512,15 +525,15 @@ int preprocess_bwd_blocks(int P) { return (P + kBwdThreads - 1) / kBwdThreads; }
 // reduction (track_update_kernel).
 int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float* means3D,
                                    const int* radii, const Camera& cam, const float* perspec,
-                                   const GeomState& g, const float* acc, float* pose_partials,
-                                   cudaStream_t stream) {
+                                   const GeomState& g, float* acc, float* pose_partials,
+                                   bool clear_acc, cudaStream_t stream) {
   if (variant != kLight) { set_error("pose-only backward exists for -light only"); return GSR_E_INVALID; }
   const int blocks = preprocess_bwd_blocks(P);
   StageScope st(ST_PRE_BWD, stream, 1);
   preprocess_bwd_kernel<kLight, 0><<<blocks, kBwdThreads, 0, stream>>>(
       P, D, M, means3D, radii, nullptr, g.clamped, nullptr, nullptr, 1.0f, g.cov3D, cam.view, cam.proj,
       cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc, g.rec, cam.W,
-      cam.H, pose_partials, GaussGradOut{}, false, true);
+      cam.H, pose_partials, GaussGradOut{}, false, true, clear_acc ? acc : nullptr);
   GSR_LAUNCH_OK(false, stream);
   return GSR_OK;
 }

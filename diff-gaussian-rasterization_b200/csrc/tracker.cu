@@ -9,7 +9,7 @@
 // kernels for the loss, the autograd graph and the optimiser — at 640x480 / 100 k Gaussians that
 // host work is longer than the rasterizer itself.
 //
-// Here one iteration is eight kernels with no host interaction, captured once in a CUDA graph and
+// Here one iteration is eight kernels (no memset, no host interaction), captured once in a CUDA graph and
 // replayed K times:
 //     preprocess_fwd -> scan_tiles -> scatter_entries -> sort_tiles        (static-capacity binning)
 //     -> render_fwd<light, fused loss>   (writes cotangents + alpha, per-tile loss partials)
@@ -98,7 +98,13 @@ track_update_kernel(int nblocks, const float* __restrict__ partials, int tiles,
                     float* loss_hist, uint32_t* tile_count, uint32_t* counters, UpdateParams up) {
   __shared__ float s_g[12];
   __shared__ float s_l[4];
+  __shared__ PoseState s_ps;   // the pose state travels through shared memory: one coalesced load /
+  __shared__ float s_persp[16];  // store instead of dozens of dependent global accesses by thread 0
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kPsWords = (int)(sizeof(PoseState) / 4);
+  if (tid >= 384 && tid < 384 + kPsWords)
+    reinterpret_cast<uint32_t*>(&s_ps)[tid - 384] = reinterpret_cast<const uint32_t*>(ps)[tid - 384];
+  if (tid >= 480 && tid < 496) s_persp[tid - 480] = persp[tid - 480];
   if (warp < 12) {
     float s = 0.f;
     for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * 12 + warp];
@@ -114,19 +120,19 @@ track_update_kernel(int nblocks, const float* __restrict__ partials, int tiles,
   }
   __syncthreads();
   if (tid == 0) {
-    const int it = ps->iter;
+    const int it = s_ps.iter;
     if (it < up.max_hist) loss_hist[it] = (s_l[0] + s_l[1]) + (s_l[2] + s_l[3]);
-    ps->iter = it + 1;
+    s_ps.iter = it + 1;
     // dL/dR[r][c] = g[3c + r], dL/dt[r] = g[9 + r]
     float dR[3][3], dt[3];
     for (int c = 0; c < 3; ++c)
       for (int r = 0; r < 3; ++r) dR[r][c] = s_g[3 * c + r];
     for (int r = 0; r < 3; ++r) dt[r] = s_g[9 + r];
     for (int c = 0; c < 4; ++c) {
-      for (int r = 0; r < 3; ++r) ps->dview[4 * c + r] = s_g[3 * c + r];
-      ps->dview[4 * c + 3] = 0.f;
+      for (int r = 0; r < 3; ++r) s_ps.dview[4 * c + r] = s_g[3 * c + r];
+      s_ps.dview[4 * c + 3] = 0.f;
     }
-    float q[4] = {ps->q[0], ps->q[1], ps->q[2], ps->q[3]};
+    float q[4] = {s_ps.q[0], s_ps.q[1], s_ps.q[2], s_ps.q[3]};
     const float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
     const float n_inv = rsqrtf(n2);
     const float w = q[0] * n_inv, x = q[1] * n_inv, y = q[2] * n_inv, z = q[3] * n_inv;
@@ -146,29 +152,29 @@ track_update_kernel(int nblocks, const float* __restrict__ partials, int tiles,
     for (int k = 0; k < 4; ++k) g[k] = (gh[k] - qh[k] * dot) * n_inv;
     for (int k = 0; k < 3; ++k) g[4 + k] = dt[k];
     // Adam (torch.optim.Adam semantics, no weight decay / amsgrad)
-    const int step = ps->step + 1;
-    ps->step = step;
+    const int step = s_ps.step + 1;
+    s_ps.step = step;
     const float bc1 = 1.f - powf(up.beta1, (float)step), bc2 = 1.f - powf(up.beta2, (float)step);
-    float p[7] = {q[0], q[1], q[2], q[3], ps->t[0], ps->t[1], ps->t[2]};
+    float p[7] = {q[0], q[1], q[2], q[3], s_ps.t[0], s_ps.t[1], s_ps.t[2]};
     for (int k = 0; k < 7; ++k) {
-      ps->grad[k] = g[k];
-      const float mk = up.beta1 * ps->m[k] + (1.f - up.beta1) * g[k];
-      const float vk = up.beta2 * ps->v[k] + (1.f - up.beta2) * g[k] * g[k];
-      ps->m[k] = mk;
-      ps->v[k] = vk;
+      s_ps.grad[k] = g[k];
+      const float mk = up.beta1 * s_ps.m[k] + (1.f - up.beta1) * g[k];
+      const float vk = up.beta2 * s_ps.v[k] + (1.f - up.beta2) * g[k] * g[k];
+      s_ps.m[k] = mk;
+      s_ps.v[k] = vk;
       const float lr = k < 4 ? up.lr_rot : up.lr_trans;
       const float denom = sqrtf(vk) / sqrtf(bc2) + up.eps;
       p[k] -= (lr / bc1) * (mk / denom);
     }
-    for (int k = 0; k < 4; ++k) ps->q[k] = p[k];
-    for (int k = 0; k < 3; ++k) ps->t[k] = p[4 + k];
-    write_camera(p, p + 4, persp, view, proj, campos);
+    for (int k = 0; k < 4; ++k) s_ps.q[k] = p[k];
+    for (int k = 0; k < 3; ++k) s_ps.t[k] = p[4 + k];
+    write_camera(p, p + 4, s_persp, view, proj, campos);
     counters[0] = 0u; counters[1] = 0u; counters[2] = 0u;  // [3] (overflow flag) is sticky
   }
   for (int i = tid; i < tiles; i += kUpdThreads) tile_count[i] = 0u;
+  __syncthreads();
+  if (tid < kPsWords) reinterpret_cast<uint32_t*>(ps)[tid] = reinterpret_cast<const uint32_t*>(&s_ps)[tid];
 }
-
-char* bump_alloc(void* ctx, size_t) { return static_cast<char*>(ctx); }
 
 }  // namespace
 
@@ -260,14 +266,14 @@ int enqueue_iteration(gsr_tracker* t, const gsr_track_params& prm, int packed_en
   if (rc != GSR_OK) return rc;
   float* acc = t->scratch;
   float* partials = t->scratch + (size_t)t->P * kAccStride;
-  GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)t->P * kAccStride * sizeof(float), s));
+  // acc is zero here: cleared once per run, then by preprocess_bwd after it has read each line
   BlendGrads cot{t->dL_dpix, t->dL_ddepth, nullptr, nullptr};
   rc = launch_render_bwd(kLight, t->camera, t->g, t->b, t->img, t->bg, t->gt_depth, t->alpha, cot, acc,
                          t->P, packed_entries, /*pose_only=*/true, false, s);
   if (rc != GSR_OK) return rc;
   const float* persp = t->cam + 36;
   rc = launch_preprocess_bwd_partials(kLight, t->P, t->D, t->M, t->means3D, t->radii, t->camera, persp,
-                                      t->g, acc, partials, s);
+                                      t->g, acc, partials, /*clear_acc=*/true, s);
   if (rc != GSR_OK) return rc;
   const int nblocks = preprocess_bwd_blocks(t->P);
   UpdateParams up{prm.lr_rot, prm.lr_trans, prm.beta1, prm.beta2, prm.eps, t->max_hist};
@@ -446,6 +452,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
     GSR_LAUNCH_OK(false, s);
     GSR_CUDA_OK(cudaMemsetAsync(t->g.counters, 0, 8 * sizeof(uint32_t), s));
     GSR_CUDA_OK(cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, s));
+    GSR_CUDA_OK(cudaMemsetAsync(t->scratch, 0, (size_t)t->P * kAccStride * sizeof(float), s));
     for (int i = 0; i < iterations; ++i) GSR_CUDA_OK(cudaGraphLaunch(t->exec, s));
     uint32_t flag[4] = {0, 0, 0, 0};
     GSR_CUDA_OK(cudaMemcpyAsync(flag, t->g.counters, sizeof(flag), cudaMemcpyDeviceToHost, s));
@@ -473,7 +480,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
     result->iterations = iterations;
     result->num_rendered = t->num_rendered;
     result->retries = retries;
-    result->kernels_per_iteration = 9;
+    result->kernels_per_iteration = 8;
   }
   return GSR_OK;
 }

@@ -17,7 +17,8 @@ import torch.nn as nn
 
 from . import _C  # noqa: F401  (hard requirement: the CUDA extension)
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
+           "set_densify_stats"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -93,6 +94,16 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_view = torch.sum(g_view, dim=0)  # [1,4,4] here ([H*W,4,4] upstream) -> [4,4]
         return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, g_view,
                 None, None)
+
+
+def set_densify_stats(grad_accum=None, denom=None, max_radii2D=None):
+    """Extension (not in the reference): register the mapping loop's densification accumulators
+    (Inria 3DGS add_densification_stats: xyz_gradient_accum [P,1], denom [P,1], max_radii2D [P],
+    fp32 CUDA) so that every following backward updates them inside its per-Gaussian kernel for the
+    visible Gaussians (radii > 0).  Call with no arguments to stop."""
+    e = torch.empty(0)
+    _C.set_densify_stats(e if grad_accum is None else grad_accum, e if denom is None else denom,
+                         e if max_radii2D is None else max_radii2D)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,

@@ -115,6 +115,16 @@ typedef struct gsr_backward_extras {
   float* dL_dcolor_masked; /* out [P,3]: dL/dcolor with the channels clamped at 0 by the forward zeroed
                               (0 for culled Gaussians); NULL = not wanted; needs SH colours */
   int skip_sh_grad;        /* 1: do not write dL_dsh */
+  /* Densification statistics of Inria-3DGS-style mapping loops, accumulated by
+   * the per-Gaussian backward kernel for every visible Gaussian (radii > 0) — what
+   * add_densification_stats does with five torch kernels over [P] after every backward:
+   *   densify_grad_accum[i] += |dL_dmean2D[i].xy|,  densify_denom[i] += 1,
+   *   max_radii2D[i] = max(max_radii2D[i], radii[i]).
+   * in/out [P] each; NULL = not wanted (grad_accum and denom only as a pair); ignored when the
+   * call computes no map gradient (-light, map_off). */
+  float* densify_grad_accum;
+  float* densify_denom;
+  float* max_radii2D;
 } gsr_backward_extras;
 
 /* ---- light variant ---------------------------------------------------------------------- */

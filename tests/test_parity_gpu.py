@@ -631,3 +631,37 @@ def test_factorized_sh_exchange_matches_summed_sh_gradients(built, variant):
         assert rel < 1e-4
     finally:
         red.detach()
+
+
+# ---- in-kernel densification statistics ------------------------------------
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_densify_stats_match_torch_accumulation(built, variant):
+    """set_densify_stats: the backward's per-Gaussian kernel accumulates |dL/dmean2D.xy|, the
+    visibility count and the largest screen radius exactly like Inria 3DGS's
+    add_densification_stats does in torch after every backward."""
+    sc, cam, scene = _scene(3000, 160, 96, seed=31, backdrop=(variant == "full"))
+    mod = built.load_variant(variant)
+    P = scene.means3D.shape[0]
+    accum = torch.zeros(P, 1, device=DEV)
+    denom = torch.zeros(P, 1, device=DEV)
+    maxr = torch.zeros(P, device=DEV)
+    want_a, want_d, want_r = np.zeros(P), np.zeros(P), np.zeros(P)
+    mod.set_densify_stats(accum, denom, maxr)
+    try:
+        for it in range(3):
+            cot = sc.make_cotangents(cam, _n_aux(variant), seed=10 + it)
+            outs, grads = pu.run_variant(mod, variant, cam, scene, cot)
+            vis = outs["radii"] > 0
+            want_a += np.where(vis, np.linalg.norm(grads["means2D"][:, :2].astype(np.float64), axis=1), 0.0)
+            want_d += vis
+            want_r = np.maximum(want_r, np.where(vis, outs["radii"], 0))
+    finally:
+        mod.set_densify_stats()
+    np.testing.assert_allclose(accum.cpu().numpy()[:, 0], want_a, rtol=1e-5, atol=1e-12)
+    np.testing.assert_array_equal(denom.cpu().numpy()[:, 0], want_d)
+    np.testing.assert_array_equal(maxr.cpu().numpy(), want_r)
+    # unregistered: a further backward leaves the accumulators alone
+    before = accum.clone()
+    pu.run_variant(mod, variant, cam, scene, sc.make_cotangents(cam, _n_aux(variant), seed=20))
+    assert torch.equal(before, accum)
