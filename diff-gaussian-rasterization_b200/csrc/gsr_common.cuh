@@ -48,6 +48,7 @@ struct Options {
   int bwd_packed;
   int async_binning;
   int track_headroom_pct;
+  int bulk_sh;
 };
 Options& options();
 
@@ -392,6 +393,58 @@ __device__ __forceinline__ void smem_to_rows(float* __restrict__ dst, const floa
     dst[ff] = smem[g * row + (ff - g * m3)];
   }
 }
+
+// ---- bulk asynchronous copies (TMA, 1-D) + mbarrier ------------------------------------------------
+// The per-Gaussian kernels move each Gaussian's SH row (12*M bytes, 16-byte aligned for M = 16 / 4)
+// between global and shared memory with cp.async.bulk: one instruction per row, no register staging,
+// completion counted in bytes on an mbarrier (loads) or by bulk groups (stores).  Only rows that are
+// needed are moved (culled Gaussians cost no SH traffic).
+__device__ __forceinline__ unsigned smem_addr_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_addr_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+// shared -> global; the issuing thread must have written the row itself (or synchronised) and
+// calls bulk_s2g_fence() between its writes and the copy
+__device__ __forceinline__ void bulk_s2g_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_addr_u32(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_s2g_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Row stride (floats) of a bulk-copied [rows, M3] slab in shared memory: a multiple of 16 bytes
+// (cp.async.bulk) and an ODD multiple, so that one LDS.128 / STS.128 per thread at the same column
+// is bank-conflict free across a quarter warp.
+__host__ __device__ constexpr int bulk_row_floats(int m3) { return ((m3 / 4) % 2 == 0) ? m3 + 4 : m3; }
 
 // Spherical-harmonics constants (real SH basis up to degree 3, standard values).
 __device__ constexpr float kSH0 = 0.28209479177387814f;

@@ -37,7 +37,10 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
   return r;
 }
 
-template <int VARIANT, int MT>  // MT: compile-time SH coefficient count (16/9/4/1) or 0 = runtime M
+// TMA == true (MT = 16 / 4 on 16-byte aligned tensors): every thread moves its own Gaussian's SH row
+// with cp.async.bulk — in only if the Gaussian is visible, awaited right before the SH backward —
+// and its dL/dSH row back out with a bulk store; no block-wide staging loops, no barriers.
+template <int VARIANT, int MT, bool TMA>  // MT: compile-time SH coefficient count (16/9/4/1) or 0 = runtime M
 __global__ void __launch_bounds__(kBwdThreads)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const int* __restrict__ radii, const float* __restrict__ shs,
@@ -49,17 +52,31 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ acc, const float4* __restrict__ g_rec, int img_w,
                       int img_h, float* __restrict__ pose_partials, GaussGradOut out,
                       bool want_gauss, bool want_pose, float* __restrict__ acc_clear) {
-  extern __shared__ float sh_smem[];  // [kBwdThreads][M*3+1] SH in, dL/dSH out
+  extern __shared__ __align__(16) float sh_smem[];  // [kBwdThreads][row] SH in, dL/dSH out
   __shared__ float s_pose[kBwdThreads / 32][12];
+  __shared__ uint64_t s_bar;
   const int base = blockIdx.x * kBwdThreads;
   const int idx = base + threadIdx.x;
-  const int row = M * 3 + 1;
+  constexpr int kBulkRow = bulk_row_floats(MT * 3);
+  constexpr unsigned kRowBytes = (unsigned)(MT * 3 * sizeof(float));
+  const int row = TMA ? kBulkRow : M * 3 + 1;
   const bool use_sh = (shs != nullptr) && want_gauss;           // SH coefficients staged in
   const bool sh_out = (shs != nullptr) && out.dL_dsh != nullptr;  // dL/dSH slab staged out
   const int nvalid = min(kBwdThreads, P - base);
-  const int nfloats = nvalid * M * 3;
+  const bool live = idx < P && radii[idx] > 0;
+  bool bar_pending = false;
 
-  if (use_sh) {
+  if (TMA) {
+    if (threadIdx.x == 0) mbar_init(&s_bar, kBwdThreads);
+    __syncthreads();
+    if (live && use_sh) {
+      mbar_arrive_expect_tx(&s_bar, kRowBytes);
+      bulk_g2s(sh_smem + threadIdx.x * kBulkRow, shs + (size_t)idx * (MT * 3), kRowBytes, &s_bar);
+    } else {
+      mbar_arrive(&s_bar);
+    }
+    bar_pending = true;
+  } else if (use_sh) {
     rows_to_smem<MT * 3>(shs + (size_t)base * M * 3, sh_smem, nvalid, M * 3, threadIdx.x, kBwdThreads);
     __syncthreads();
   }
@@ -68,7 +85,6 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 #pragma unroll
   for (int k = 0; k < 12; ++k) pose[k] = 0.f;
 
-  const bool live = idx < P && radii[idx] > 0;
   float* my_sh = sh_smem + threadIdx.x * row;
 
   // culled Gaussians — and, in -light's tracking mode (map_off), all of them — get exact zeros
@@ -89,7 +105,13 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
     if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sh_out) {
-      for (int k = 0; k < M * 3; ++k) my_sh[k] = 0.f;
+      if (TMA) {
+        // (no wait needed: nothing is in flight towards this thread's own row)
+#pragma unroll
+        for (int v = 0; v < MT * 3 / 4; ++v) reinterpret_cast<float4*>(my_sh)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int k = 0; k < M * 3; ++k) my_sh[k] = 0.f;
+      }
     }
   }
 
@@ -238,7 +260,18 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 #pragma unroll
         for (int k = 0; k < 16; ++k) coef[k] = 0.f;
         coef[0] = kSH0;
-#define SH(k, ch) my_sh[3 * (k) + (ch)]
+        // TMA: wait for this block's rows, then pull the own row into registers with LDS.128
+        constexpr int kShRegs = TMA ? (MT > 0 ? MT * 3 : 4) : 4;
+        float shr[kShRegs];
+        if (TMA) {
+          if (bar_pending) { mbar_wait(&s_bar, 0u); bar_pending = false; }
+#pragma unroll
+          for (int v = 0; v < kShRegs / 4; ++v) {
+            const float4 q4 = reinterpret_cast<const float4*>(my_sh)[v];
+            shr[4 * v + 0] = q4.x; shr[4 * v + 1] = q4.y; shr[4 * v + 2] = q4.z; shr[4 * v + 3] = q4.w;
+          }
+        }
+#define SH(k, ch) (TMA ? shr[(3 * (k) + (ch)) < kShRegs ? (3 * (k) + (ch)) : 0] : my_sh[3 * (k) + (ch)])
         if (D > 0) {
           coef[1] = -kSH1 * y; coef[2] = kSH1 * z; coef[3] = -kSH1 * x;
 #pragma unroll
@@ -285,11 +318,25 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         }
 #undef SH
         const int ncoef = (D + 1) * (D + 1);
-        for (int k = 0; k < M; ++k) {
-          const float ck = (k < ncoef && k < 16) ? coef[k] : 0.f;
-          my_sh[3 * k + 0] = ck * dR[0];
-          my_sh[3 * k + 1] = ck * dR[1];
-          my_sh[3 * k + 2] = ck * dR[2];
+        if (TMA) {
+          if (sh_out) {
+            float o[kShRegs];
+#pragma unroll
+            for (int k = 0; k < kShRegs / 3; ++k) {
+              const float ck = (k < ncoef && k < 16) ? coef[k < 16 ? k : 0] : 0.f;
+              o[3 * k + 0] = ck * dR[0]; o[3 * k + 1] = ck * dR[1]; o[3 * k + 2] = ck * dR[2];
+            }
+#pragma unroll
+            for (int v = 0; v < kShRegs / 4; ++v)
+              reinterpret_cast<float4*>(my_sh)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          }
+        } else {
+          for (int k = 0; k < M; ++k) {
+            const float ck = (k < ncoef && k < 16) ? coef[k] : 0.f;
+            my_sh[3 * k + 0] = ck * dR[0];
+            my_sh[3 * k + 1] = ck * dR[1];
+            my_sh[3 * k + 2] = ck * dR[2];
+          }
         }
         const float3 dL_ddir = make_float3(dx_[0] * dR[0] + dx_[1] * dR[1] + dx_[2] * dR[2],
                                            dy_[0] * dR[0] + dy_[1] * dR[1] + dy_[2] * dR[2],
@@ -416,8 +463,14 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     }
   }
 
-  // coalesced store of the block's dL/dSH slab
-  if (sh_out) {
+  // dL/dSH out: one bulk store per thread of its own row (TMA) / coalesced store of the block's slab
+  if (TMA) {
+    if (bar_pending) mbar_wait(&s_bar, 0u);  // the block's shared memory must outlive the loads in flight
+    if (sh_out && idx < P) {
+      bulk_s2g_fence();
+      bulk_s2g(out.dL_dsh + (size_t)idx * (MT * 3), my_sh, kRowBytes);
+    }
+  } else if (sh_out) {
     __syncthreads();
     smem_to_rows<MT * 3>(out.dL_dsh + (size_t)base * M * 3, sh_smem, nvalid, M * 3, threadIdx.x,
                          kBwdThreads);
@@ -440,6 +493,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       pose_partials[(size_t)blockIdx.x * 12 + threadIdx.x] = s;
     }
   }
+  if (TMA && sh_out && idx < P) bulk_s2g_wait_read();
 }
 
 // Adds the per-block pose partials in a fixed order (deterministic, no atomics) and scatters the
@@ -480,7 +534,12 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
                           const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
                           cudaStream_t stream) {
   const int blocks = (P + kBwdThreads - 1) / kBwdThreads;
-  const size_t smem = (shs != nullptr) ? sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1) : 0;
+  const bool tma = shs != nullptr && (M == 16 || M == 4) && options().bulk_sh != 0 &&
+                   (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                   (out.dL_dsh == nullptr || (reinterpret_cast<uintptr_t>(out.dL_dsh) & 15) == 0);
+  const size_t smem = shs == nullptr ? 0
+                      : tma          ? sizeof(float) * kBwdThreads * (size_t)bulk_row_floats(M * 3)
+                                     : sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1);
   const float* cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
   StageScope st(ST_PRE_BWD, stream, 2);
   // With want_gauss == false (-light, map_off: light backward.cu:593,609,654,666;
@@ -489,20 +548,24 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
     GSR_CUDA_OK(cudaMemsetAsync(out.dL_dsh, 0, sizeof(float) * 3 * (size_t)P * (size_t)M, stream));
   }
   {
-#define GSR_PRE_BWD(V, MT)                                                                       \
-  cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+#define GSR_PRE_BWD(V, MT, TMA)                                                                  \
+  cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                        cudaSharedmemCarveoutMaxShared);                                          \
-  preprocess_bwd_kernel<V, MT><<<blocks, kBwdThreads, smem, stream>>>(                           \
+  preprocess_bwd_kernel<V, MT, TMA><<<blocks, kBwdThreads, smem, stream>>>(                      \
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
       g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr)
 #define GSR_PRE_BWD_M(V)                                                                         \
-  switch (M) {                                                                                   \
-    case 16: GSR_PRE_BWD(V, 16); break;                                                          \
-    case 9: GSR_PRE_BWD(V, 9); break;                                                            \
-    case 4: GSR_PRE_BWD(V, 4); break;                                                            \
-    case 1: GSR_PRE_BWD(V, 1); break;                                                            \
-    default: GSR_PRE_BWD(V, 0); break;                                                           \
+  if (tma) {                                                                                     \
+    if (M == 16) { GSR_PRE_BWD(V, 16, true); } else { GSR_PRE_BWD(V, 4, true); }                 \
+  } else {                                                                                       \
+    switch (M) {                                                                                 \
+      case 16: GSR_PRE_BWD(V, 16, false); break;                                                 \
+      case 9: GSR_PRE_BWD(V, 9, false); break;                                                   \
+      case 4: GSR_PRE_BWD(V, 4, false); break;                                                   \
+      case 1: GSR_PRE_BWD(V, 1, false); break;                                                   \
+      default: GSR_PRE_BWD(V, 0, false); break;                                                  \
+    }                                                                                            \
   }
     if (variant == kLight) {
       GSR_PRE_BWD_M(kLight)
@@ -530,7 +593,7 @@ int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float
   if (variant != kLight) { set_error("pose-only backward exists for -light only"); return GSR_E_INVALID; }
   const int blocks = preprocess_bwd_blocks(P);
   StageScope st(ST_PRE_BWD, stream, 1);
-  preprocess_bwd_kernel<kLight, 0><<<blocks, kBwdThreads, 0, stream>>>(
+  preprocess_bwd_kernel<kLight, 0, false><<<blocks, kBwdThreads, 0, stream>>>(
       P, D, M, means3D, radii, nullptr, g.clamped, nullptr, nullptr, 1.0f, g.cov3D, cam.view, cam.proj,
       cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc, g.rec, cam.W,
       cam.H, pose_partials, GaussGradOut{}, false, true, clear_acc ? acc : nullptr);

@@ -157,13 +157,27 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 pos, const flo
   return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
 }
 
+// same evaluation from a bulk-copied row: the row is pulled into registers with LDS.128 first
+template <int MT>
+__device__ __forceinline__ float3 sh_to_rgb_row(int deg, const float3 pos, const float3 campos,
+                                                const float* __restrict__ row, unsigned char& clamp_bits) {
+  float sh[MT * 3];
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int v = 0; v < MT * 3 / 4; ++v) {
+    const float4 q = r4[v];
+    sh[4 * v + 0] = q.x; sh[4 * v + 1] = q.y; sh[4 * v + 2] = q.z; sh[4 * v + 3] = q.w;
+  }
+  return sh_to_rgb(deg, pos, campos, sh, clamp_bits);
+}
+
 constexpr int kPreThreads = 128;
 constexpr int kMaxCoeffs = 16;
 
 // SH coefficients of a block of Gaussians are contiguous in memory ([P, M, 3] fp32): the block
 // streams its slab with coalesced 128-bit loads into shared memory (row stride M*3+1 floats to
 // spread banks) and each thread then reads its own row.
-template <int MT>  // compile-time number of SH coefficients (16 / 9 / 4 / 1) or 0 = runtime M
+template <int MT, bool TMA>  // MT: compile-time number of SH coefficients (16 / 9 / 4 / 1) or 0 = runtime M
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ scales, float scale_modifier,
@@ -176,26 +190,44 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                       uint2* __restrict__ rects, uint32_t* __restrict__ tile_count,
                       bool prefiltered, bool tight_tiles) {
-  extern __shared__ float sh_smem[];  // [kPreThreads][M*3+1] when shs != nullptr
+  // TMA == false: [kPreThreads][M*3+1] slab staged with coalesced loads by the whole block.
+  // TMA == true : [kPreThreads][bulk_row_floats(M*3)] rows, each fetched by its own thread with one
+  //               cp.async.bulk AFTER the cull tests (culled Gaussians cost no SH traffic) and
+  //               awaited only where the colour is evaluated.
+  extern __shared__ __align__(16) float sh_smem[];
+  __shared__ uint64_t s_bar;
   const int base = blockIdx.x * kPreThreads;
   const int idx = base + threadIdx.x;
-  const int row = M * 3 + 1;
+  constexpr int kBulkRow = bulk_row_floats(MT * 3);
+  const int row = TMA ? kBulkRow : M * 3 + 1;
+  const bool sh_path = shs != nullptr && colors_precomp == nullptr;
 
-  if (shs != nullptr && colors_precomp == nullptr) {
-    rows_to_smem<MT * 3>(shs + (size_t)base * M * 3, sh_smem, min(kPreThreads, P - base), M * 3,
-                         threadIdx.x, kPreThreads);
+  if (TMA) {
+    if (threadIdx.x == 0) mbar_init(&s_bar, kPreThreads);
     __syncthreads();
+  } else {
+    if (sh_path) {
+      rows_to_smem<MT * 3>(shs + (size_t)base * M * 3, sh_smem, min(kPreThreads, P - base), M * 3,
+                           threadIdx.x, kPreThreads);
+      __syncthreads();
+    }
+    if (idx >= P) return;
   }
-  if (idx >= P) return;
 
   int my_radius_i = 0;
   uint32_t my_tiles = 0;
   uint2 my_rect = make_uint2(0u, 0u);
   unsigned char cbits = 0;
+  bool live = false;
+  float3 p_orig = make_float3(0.f, 0.f, 0.f);
+  float2 pix = make_float2(0.f, 0.f);
+  float3 conic = make_float3(0.f, 0.f, 0.f);
+  float opacity = 0.f, power_cut = 0.f, depth = 0.f;
+  uint2 rmin = make_uint2(0u, 0u), rmax = make_uint2(0u, 0u);
 
-  const float3 p_orig = ld3(means3D, idx);
-  const float3 p_view = xform_point_4x3(p_orig, view);
-  do {
+  if (idx < P) do {
+    p_orig = ld3(means3D, idx);
+    const float3 p_view = xform_point_4x3(p_orig, view);
     if (p_view.z <= 0.2f) {  // near cull (auxiliary.h:154); lateral cull is disabled upstream
       if (prefiltered) {
         printf("Point is filtered although prefiltered is set. This shouldn't happen!");
@@ -203,6 +235,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       }
       break;
     }
+    depth = p_view.z;
     const float4 p_hom = xform_point_4x4(p_orig, proj);
     const float p_w = GSR_RCP(GSR_ADD(p_hom.w, 0.0000001f));
     const float3 p_proj = make_float3(GSR_MUL(p_hom.x, p_w), GSR_MUL(p_hom.y, p_w), GSR_MUL(p_hom.z, p_w));
@@ -224,32 +257,38 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     const float det = GSR_FMA(cov.x, cov.z, -GSR_MUL(cov.y, cov.y));
     if (det == 0.0f) break;
     const float det_inv = GSR_RCP(det);
-    const float3 conic = make_float3(GSR_MUL(cov.z, det_inv), GSR_MUL(cov.y, -det_inv), GSR_MUL(cov.x, det_inv));
+    conic = make_float3(GSR_MUL(cov.z, det_inv), GSR_MUL(cov.y, -det_inv), GSR_MUL(cov.x, det_inv));
 
     const float mid = GSR_MUL(0.5f, GSR_ADD(cov.x, cov.z));
     const float disc = GSR_SQRT(fmaxf(0.1f, GSR_FMA(mid, mid, -det)));
     const float lambda1 = GSR_ADD(mid, disc);
     const float lambda2 = GSR_SUB(mid, disc);
     const float my_radius = ceilf(GSR_MUL(3.f, GSR_SQRT(fmaxf(lambda1, lambda2))));
-    const float2 pix = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
-    uint2 rmin, rmax;
+    pix = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
     tile_rect(pix.x, pix.y, (int)my_radius, grid_x, grid_y, rmin, rmax);
     if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) break;
+    my_radius_i = (int)my_radius;
+    live = true;
+  } while (false);
 
-    float3 rgb;
-    if (colors_precomp == nullptr) {
-      const float3 campos = make_float3(campos_p[0], campos_p[1], campos_p[2]);
-      rgb = sh_to_rgb(D, p_orig, campos, sh_smem + threadIdx.x * row, cbits);
+  // the SH row of a surviving Gaussian starts its way to shared memory now; everything up to the
+  // colour evaluation overlaps the copy
+  if (TMA) {
+    if (live && sh_path) {
+      mbar_arrive_expect_tx(&s_bar, (unsigned)(MT * 3 * sizeof(float)));
+      bulk_g2s(sh_smem + threadIdx.x * kBulkRow, shs + (size_t)idx * (MT * 3),
+               (unsigned)(MT * 3 * sizeof(float)), &s_bar);
     } else {
-      rgb = ld3(colors_precomp, idx);
+      mbar_arrive(&s_bar);
     }
-    const float opacity = opacities[idx];
+  }
+
+  if (live) {
+    opacity = opacities[idx];
     // power_cut: pairs with power < power_cut cannot reach alpha >= 15/255 (opacity*exp(power)
     // is monotone in power); the 1e-3 margin (0.1 % in alpha) is four orders of magnitude above
     // the rounding error of the exact test that still runs for everything above the cut.
-    const float power_cut = (opacity > 0.0f) ? (logf(kAlphaMin / opacity) - 1e-3f) : 1.0f;
-
-    my_radius_i = (int)my_radius;
+    power_cut = (opacity > 0.0f) ? (logf(kAlphaMin / opacity) - 1e-3f) : 1.0f;
     if (tight_tiles) {
       // shrink the reference's 3-sigma rectangle to the tiles the alpha >= 15/255 ellipse can reach:
       // tile t holds pixel centres [16t, 16t+15]
@@ -275,14 +314,31 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         for (uint32_t x = rmin.x; x < rmax.x; ++x) atomicAdd(tile_count + y * (uint32_t)grid_x + x, 1u);
     }
     rec[3 * (size_t)idx + 0] = make_float4(pix.x, pix.y, conic.x, conic.y);
-    rec[3 * (size_t)idx + 1] = make_float4(conic.z, opacity, power_cut, p_view.z);
-    rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
-  } while (false);
+    rec[3 * (size_t)idx + 1] = make_float4(conic.z, opacity, power_cut, depth);
+  }
+  if (idx < P) {
+    radii[idx] = my_radius_i;
+    tiles_touched[idx] = my_tiles;
+    rects[idx] = my_rect;
+  }
 
-  radii[idx] = my_radius_i;
-  tiles_touched[idx] = my_tiles;
-  rects[idx] = my_rect;
-  clamped[idx] = cbits;
+  // every thread waits: the block's shared memory must outlive the copies in flight
+  if (TMA) mbar_wait(&s_bar, 0u);
+
+  if (live) {
+    float3 rgb;
+    if (colors_precomp == nullptr) {
+      const float3 campos = make_float3(campos_p[0], campos_p[1], campos_p[2]);
+      if (TMA)
+        rgb = sh_to_rgb_row<(MT > 0 ? MT : 1)>(D, p_orig, campos, sh_smem + threadIdx.x * kBulkRow, cbits);
+      else
+        rgb = sh_to_rgb(D, p_orig, campos, sh_smem + threadIdx.x * row, cbits);
+    } else {
+      rgb = ld3(colors_precomp, idx);
+    }
+    rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+  }
+  if (idx < P) clamped[idx] = cbits;
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -310,24 +366,33 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
     set_error("SH degree %d needs %d coefficients but M = %d", D, (D + 1) * (D + 1), M);
     return GSR_E_INVALID;
   }
-  const size_t smem = (shs != nullptr && colors_precomp == nullptr)
-                          ? sizeof(float) * kPreThreads * (size_t)(M * 3 + 1) : 0;
+  const bool sh_path = shs != nullptr && colors_precomp == nullptr;
+  // bulk-copied SH rows need 16-byte aligned rows: M = 16 or 4 on a 16-byte aligned tensor
+  const bool tma = sh_path && (M == 16 || M == 4) && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                   options().bulk_sh != 0;
+  const size_t smem = !sh_path ? 0
+                      : tma    ? sizeof(float) * kPreThreads * (size_t)bulk_row_floats(M * 3)
+                               : sizeof(float) * kPreThreads * (size_t)(M * 3 + 1);
   const int blocks = (P + kPreThreads - 1) / kPreThreads;
   StageScope st(ST_PRE_FWD, stream);
-#define GSR_PRE_FWD(MT)                                                                          \
-  cudaFuncSetAttribute(preprocess_fwd_kernel<MT>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+#define GSR_PRE_FWD(MT, TMA)                                                                     \
+  cudaFuncSetAttribute(preprocess_fwd_kernel<MT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                        cudaSharedmemCarveoutMaxShared);                                          \
-  preprocess_fwd_kernel<MT><<<blocks, kPreThreads, smem, stream>>>(                              \
+  preprocess_fwd_kernel<MT, TMA><<<blocks, kPreThreads, smem, stream>>>(                         \
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,        \
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,  \
       cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,        \
       g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0)
-  switch (M) {
-    case 16: GSR_PRE_FWD(16); break;
-    case 9: GSR_PRE_FWD(9); break;
-    case 4: GSR_PRE_FWD(4); break;
-    case 1: GSR_PRE_FWD(1); break;
-    default: GSR_PRE_FWD(0); break;
+  if (tma) {
+    if (M == 16) { GSR_PRE_FWD(16, true); } else { GSR_PRE_FWD(4, true); }
+  } else {
+    switch (M) {
+      case 16: GSR_PRE_FWD(16, false); break;
+      case 9: GSR_PRE_FWD(9, false); break;
+      case 4: GSR_PRE_FWD(4, false); break;
+      case 1: GSR_PRE_FWD(1, false); break;
+      default: GSR_PRE_FWD(0, false); break;
+    }
   }
 #undef GSR_PRE_FWD
   GSR_LAUNCH_OK(debug, stream);

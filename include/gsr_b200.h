@@ -89,6 +89,9 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   the host has read this frame's count, so the GPU does not idle during the
  *                   read-back (guarded kernels; the binning is redone when the estimate was too
  *                   small); 0: wait for the count first, exact buffer size.
+ *   "bulk_sh"       1 (default): the per-Gaussian kernels move SH rows (M = 16 or 4, 16-byte aligned)
+ *                   between global and shared memory with cp.async.bulk (TMA), one row per thread and
+ *                   only for Gaussians that survive culling; 0: block-wide coalesced staging.
  *   "track_headroom_pct" head room (percent, default 50) of the tracker's binning buffer over the
  *                   counts of its probing forward; negative values force the overflow / retry path
  *                   (test hook).
