@@ -42,6 +42,7 @@ struct PoseState {      // device resident
   float v[8];           // Adam second moment
   float grad[8];        // dL/dq, dL/dt of the last iteration
   float dview[16];      // dL/dviewmatrix of the last iteration (reference layout)
+  float twist[8];       // dL/d(xi) of the last iteration, xi = (omega, v): W2C' = exp(xi^) W2C
   int step;             // Adam step count
   int iter;             // iterations run since the last reset of the loss history
   int pad1[2];
@@ -131,6 +132,24 @@ track_update_kernel(int nblocks, const float* __restrict__ partials, int tiles,
     for (int c = 0; c < 4; ++c) {
       for (int r = 0; r < 3; ++r) s_ps.dview[4 * c + r] = s_g[3 * c + r];
       s_ps.dview[4 * c + 3] = 0.f;
+    }
+    // SE(3) tangent-space projection (left perturbation W2C' = exp(xi^) W2C, xi = (omega, v)):
+    //   dL/dv = dL/dt,   dL/domega = sum_c R[:,c] x dL/dR[:,c] + t x dL/dt
+    {
+      float Rm[3][3];
+      const float ni = rsqrtf(s_ps.q[0] * s_ps.q[0] + s_ps.q[1] * s_ps.q[1] + s_ps.q[2] * s_ps.q[2] +
+                              s_ps.q[3] * s_ps.q[3]);
+      quat_to_R(s_ps.q, ni, Rm);
+      float om[3] = {0.f, 0.f, 0.f};
+      for (int c = 0; c < 4; ++c) {
+        const float a0 = c < 3 ? Rm[0][c] : s_ps.t[0], a1 = c < 3 ? Rm[1][c] : s_ps.t[1],
+                    a2 = c < 3 ? Rm[2][c] : s_ps.t[2];
+        const float b0 = c < 3 ? dR[0][c] : dt[0], b1 = c < 3 ? dR[1][c] : dt[1], b2 = c < 3 ? dR[2][c] : dt[2];
+        om[0] += a1 * b2 - a2 * b1;
+        om[1] += a2 * b0 - a0 * b2;
+        om[2] += a0 * b1 - a1 * b0;
+      }
+      for (int k = 0; k < 3; ++k) { s_ps.twist[k] = om[k]; s_ps.twist[3 + k] = dt[k]; }
     }
     float q[4] = {s_ps.q[0], s_ps.q[1], s_ps.q[2], s_ps.q[3]};
     const float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
@@ -477,6 +496,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
     for (int k = 0; k < 3; ++k) result->t[k] = fin.t[k];
     for (int k = 0; k < 16; ++k) result->last_dL_dview[k] = fin.dview[k];
     for (int k = 0; k < 7; ++k) result->last_grad[k] = fin.grad[k];
+    for (int k = 0; k < 6; ++k) result->last_twist_grad[k] = fin.twist[k];
     result->iterations = iterations;
     result->num_rendered = t->num_rendered;
     result->retries = retries;

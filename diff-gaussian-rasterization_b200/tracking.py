@@ -32,6 +32,7 @@ class TrackParams(ctypes.Structure):
 class TrackResult(ctypes.Structure):
     _fields_ = [("q", ctypes.c_float * 4), ("t", ctypes.c_float * 3),
                 ("last_dL_dview", ctypes.c_float * 16), ("last_grad", ctypes.c_float * 7),
+                ("last_twist_grad", ctypes.c_float * 6),
                 ("iterations", ctypes.c_int), ("num_rendered", ctypes.c_int),
                 ("retries", ctypes.c_int), ("kernels_per_iteration", ctypes.c_int)]
 
@@ -140,7 +141,8 @@ class PoseTracker:
         res = TrackResult()
         _check(_lib().gsr_tracker_run(self._h, ctypes.byref(cp), int(iterations), hist, ctypes.byref(res)))
         return dict(q=list(res.q), t=list(res.t), loss=list(hist), last_dL_dview=list(res.last_dL_dview),
-                    last_grad=list(res.last_grad), num_rendered=res.num_rendered, retries=res.retries,
+                    last_grad=list(res.last_grad), last_twist_grad=list(res.last_twist_grad),
+                    num_rendered=res.num_rendered, retries=res.retries,
                     kernels_per_iteration=res.kernels_per_iteration)
 
 

@@ -251,6 +251,8 @@ typedef struct gsr_track_result {
   float q[4], t[3];            /* pose after the last iteration */
   float last_dL_dview[16];     /* dL/dviewmatrix of the last iteration (reference layout, before the step) */
   float last_grad[7];          /* dL/dq[4], dL/dt[3] of the last iteration */
+  float last_twist_grad[6];    /* the same gradient projected on the SE(3) tangent space: dL/d(omega, v)
+                                  for the left perturbation W2C' = exp(xi^) W2C */
   int iterations;              /* iterations run */
   int num_rendered;            /* (Gaussian, tile) duplicates of the probing forward at the start pose */
   int retries;                 /* reruns after a binning-buffer overflow */

@@ -47,6 +47,15 @@ def pose_gradient(q, dL_dview):
     return (gh - qh * (qh @ gh)) / n, dt
 
 
+def twist_gradient(q, t, dL_dview):
+    """dL/d(omega, v) for the left perturbation W2C' = exp(xi^) W2C (SE(3) tangent space)."""
+    g = np.asarray(dL_dview, dtype=np.float64).reshape(4, 4)
+    dR, dt = g[:3, :3].T, g[3, :3]
+    R = quat_to_R(q)
+    om = sum(np.cross(R[:, c], dR[:, c]) for c in range(3)) + np.cross(np.asarray(t, dtype=np.float64), dt)
+    return np.concatenate([om, dt])
+
+
 class Adam:
     """torch.optim.Adam (no weight decay, no amsgrad) on a 7-vector with two learning rates."""
 

@@ -49,6 +49,37 @@ def test_pose_gradient_matches_autograd(seed):
     np.testing.assert_allclose(gt, t.grad.numpy(), rtol=1e-10, atol=1e-12)
 
 
+def _so3_exp(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_twist_gradient_matches_finite_differences(seed):
+    """dL/d(omega, v) of L = <dview, (exp(xi^) W2C)^T> at xi = 0, by central differences."""
+    q0, t0 = _random_pose(seed)
+    rng = np.random.default_rng(200 + seed)
+    dview = rng.normal(size=(4, 4))
+    dview[:, 3] = 0.0
+    R = po.quat_to_R(q0)
+
+    def L(xi):
+        Re = _so3_exp(xi[:3])
+        w2c = np.eye(4)
+        w2c[:3, :3] = Re @ R
+        w2c[:3, 3] = Re @ t0 + xi[3:]   # first order in xi (V(omega) v = v + O(|xi|^2))
+        return float((w2c.T * dview).sum())
+    fd = np.zeros(6)
+    for k in range(6):
+        e = np.zeros(6)
+        e[k] = 1e-6
+        fd[k] = (L(e) - L(-e)) / 2e-6
+    np.testing.assert_allclose(po.twist_gradient(q0, t0, dview.reshape(-1)), fd, rtol=1e-6, atol=1e-8)
+
+
 def test_adam_matches_torch():
     rng = np.random.default_rng(7)
     p0 = rng.normal(size=7)
@@ -102,4 +133,4 @@ def test_tracker_symbols_exported():
                  "gsr_tracker_set_frame", "gsr_tracker_set_pose", "gsr_tracker_run"):
         assert hasattr(lib, name), name
     assert ctypes.sizeof(trk.TrackParams) == 36
-    assert ctypes.sizeof(trk.TrackResult) == 4 * (4 + 3 + 16 + 7 + 4)
+    assert ctypes.sizeof(trk.TrackResult) == 4 * (4 + 3 + 16 + 7 + 6 + 4)

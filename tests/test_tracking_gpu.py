@@ -99,6 +99,7 @@ def test_first_iteration_matches_torch_loop_and_oracle(built, use_sh):
     po = ge.load_pose_oracle()
     gq, gt = po.pose_gradient(s["q0"], got["last_dL_dview"])
     assert _rel(got["last_grad"], np.concatenate([gq, gt])) <= 1e-5
+    assert _rel(got["last_twist_grad"], po.twist_gradient(s["q0"], s["t0"], got["last_dL_dview"])) <= 1e-5
     p1 = po.Adam(4e-4, 2e-3).step(np.array(s["q0"] + s["t0"], dtype=np.float64), np.concatenate([gq, gt]))
     np.testing.assert_allclose(got["q"] + got["t"], p1, atol=2e-6)
     trk.close()
