@@ -15,7 +15,7 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -163,7 +163,7 @@ int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinS
     StageScope st(ST_MEMSET, a.stream, 2);
     GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
     if (tile_local)
-      GSR_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, a.stream));
+      GSR_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles * cnt_stride(), a.stream));
   }
   int rc = launch_preprocess_fwd(a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations,
                                  a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, cam,
@@ -213,6 +213,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "async_binning")) return &g_opts.async_binning;
   if (!strcmp(key, "track_headroom_pct")) return &g_opts.track_headroom_pct;
   if (!strcmp(key, "bulk_sh")) return &g_opts.bulk_sh;
+  if (!strcmp(key, "cnt_stride")) return &g_opts.cnt_stride;
   return nullptr;
 }
 

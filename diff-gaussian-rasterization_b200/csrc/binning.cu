@@ -61,8 +61,8 @@ size_t ImgState::carve(ImgState& s, char* base, int HW, int tiles, int variant) 
   Carver c(base);
   s.ranges = c.take<uint2>((size_t)tiles);
   s.tile_last = c.take<uint32_t>((size_t)tiles);
-  s.tile_count = c.take<uint32_t>((size_t)tiles);
-  s.tile_fill = c.take<uint32_t>((size_t)tiles);
+  s.tile_count = c.take<uint32_t>((size_t)tiles * kCntStrideMax);
+  s.tile_fill = c.take<uint32_t>((size_t)tiles * kCntStrideMax);
   s.n_contrib = c.take<uint32_t>((size_t)HW);
   if (variant == kFull) {
     s.final_T = c.take<float>((size_t)HW);
@@ -148,16 +148,30 @@ constexpr int kTileSortThreads = 256;
 __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
                   uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ counters,
-                  uint32_t capacity, uint32_t longest_cap) {
+                  uint32_t capacity, uint32_t longest_cap, int cs) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry, s_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { s_carry = 0; s_max = 0; }
   __syncthreads();
   uint32_t local_max = 0;
-  for (int base = 0; base < tiles; base += 1024) {
+  // the (strided) counter loads of the first rounds are issued up front: one latency, not eight
+  constexpr int kPre = 8;
+  uint32_t pre[kPre];
+#pragma unroll
+  for (int r = 0; r < kPre; ++r) {
+    const int t = r * 1024 + tid;
+    pre[r] = (t < tiles) ? tile_count[(size_t)t * cs] : 0u;
+  }
+  for (int base = 0, r = 0; base < tiles; base += 1024, ++r) {
     const int t = base + tid;
-    const uint32_t c = (t < tiles) ? tile_count[t] : 0u;
+    uint32_t c = 0u;
+    if (r < kPre) {
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) if (q == r) c = pre[q];
+    } else if (t < tiles) {
+      c = tile_count[(size_t)t * cs];
+    }
     local_max = max(local_max, c);
     uint32_t incl = c;
 #pragma unroll
@@ -181,7 +195,7 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
     const uint32_t start = carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
     if (t < tiles) {
       ranges[t] = make_uint2(min(start, capacity), min(start + min(c, longest_cap), capacity));
-      tile_fill[t] = start;  // scatter cursor
+      tile_fill[(size_t)t * cs] = start;  // scatter cursor
     }
     __syncthreads();
     if (tid == 1023) s_carry = carry + s_warp[31];
@@ -206,7 +220,7 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
                                        const uint32_t* __restrict__ tiles_touched,
                                        const uint2* __restrict__ rects, int grid_x,
                                        uint32_t* __restrict__ tile_fill,
-                                       uint64_t* __restrict__ entries, uint32_t capacity) {
+                                       uint64_t* __restrict__ entries, uint32_t capacity, uint32_t cs) {
   // `capacity` = entries the buffer can hold.  It only bites when the buffer was sized from the
   // previous frame's count (speculative launch, see run_binning) and this frame has more: the
   // surplus is dropped and the host, which sees the real count, redoes the binning.
@@ -237,7 +251,7 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
 #pragma unroll
       for (uint32_t u = 0; u < 4; ++u) {
         const uint32_t q = q0 + 32u * u;
-        if (q < total) slot[u] = atomicAdd(tile_fill + (y0 + q / w) * (uint32_t)grid_x + x0 + q % w, 1u);
+        if (q < total) slot[u] = atomicAdd(tile_fill + ((y0 + q / w) * (uint32_t)grid_x + x0 + q % w) * cs, 1u);
       }
 #pragma unroll
       for (uint32_t u = 0; u < 4; ++u)
@@ -251,7 +265,7 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
     uint32_t slots[kWide];
 #pragma unroll
     for (uint32_t u = 0; u < kWide; ++u)  // issue all atomics first, then the dependent stores
-      if (u < n) slots[u] = atomicAdd(tile_fill + (y0 + u / w) * (uint32_t)grid_x + x0 + u % w, 1u);
+      if (u < n) slots[u] = atomicAdd(tile_fill + ((y0 + u / w) * (uint32_t)grid_x + x0 + u % w) * cs, 1u);
 #pragma unroll
     for (uint32_t u = 0; u < kWide; ++u)
       if (u < n && slots[u] < capacity) entries[slots[u]] = entry;
@@ -408,7 +422,8 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
   {
     StageScope st(ST_EMIT, stream);
     scatter_entries_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
-        P, g.rec, g.tiles_touched, g.rect, cam.grid_x, img.tile_fill, b.keys_unsorted, capacity);
+        P, g.rec, g.tiles_touched, g.rect, cam.grid_x, img.tile_fill, b.keys_unsorted, capacity,
+        (uint32_t)cnt_stride());
     GSR_LAUNCH_OK(debug, stream);
   }
   {
@@ -441,7 +456,7 @@ int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgS
   {
     StageScope st(ST_SCAN, stream, 1);
     scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
-                                              g.counters, capacity, longest_cap);
+                                              g.counters, capacity, longest_cap, cnt_stride());
     GSR_LAUNCH_OK(false, stream);
   }
   return launch_tile_sort(cam, P, g, img, b, capacity, longest_cap, false, stream);
@@ -451,7 +466,7 @@ int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgS
 // in g.counters[2] for the caller to read back.
 int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream_t stream) {
   scan_tiles_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges,
-                                            img.tile_fill, g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                                            img.tile_fill, g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride());
   GSR_LAUNCH_OK(false, stream);
   return GSR_OK;
 }
@@ -469,7 +484,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
       // img.tile_count was filled by preprocess_fwd (one red per duplicate)
       StageScope st(ST_SCAN, stream, 1);
       scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
-                                                g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                                                g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride());
       GSR_LAUNCH_OK(debug, stream);
     }
     // The one host<->device synchronisation of the forward: the duplicate count sizes the binning
@@ -509,7 +524,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
           // estimate too small: reset the scatter cursors (the scan rewrites them) and fall through
           StageScope st(ST_SCAN, stream, 1);
           scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
-                                                    g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                                                    g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride());
           GSR_LAUNCH_OK(debug, stream);
         }
       }

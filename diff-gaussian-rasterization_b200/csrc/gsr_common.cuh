@@ -22,6 +22,8 @@ constexpr float kAlphaMin = 15.0f / 255.0f;    // reference forward.cu:360 (Inri
 constexpr float kAlphaMax = 0.99f;
 constexpr float kTmin = 0.0001f;
 constexpr int kAccStride = 16;                 // floats per Gaussian in the backward accumulator
+constexpr int kCntStrideMax = 32;              // the per-tile counters / cursors may be spread one per 32-byte
+                                               // sector (option "cnt_stride") to relieve same-line atomics
 
 enum Variant { kLight = 0, kFull = 1 };
 
@@ -49,8 +51,10 @@ struct Options {
   int async_binning;
   int track_headroom_pct;
   int bulk_sh;
+  int cnt_stride;
 };
 Options& options();
+inline int cnt_stride() { const int s = options().cnt_stride; return (s >= 1 && s <= kCntStrideMax) ? s : 1; }
 
 // ---- stage timing (gsr_stage_times in the C ABI) ---------------------------------------------
 enum Stage {

@@ -189,7 +189,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int* __restrict__ radii, float4* __restrict__ rec, float* __restrict__ cov3Ds,
                       unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                       uint2* __restrict__ rects, uint32_t* __restrict__ tile_count,
-                      bool prefiltered, bool tight_tiles) {
+                      bool prefiltered, bool tight_tiles, uint32_t cs) {
   // TMA == false: [kPreThreads][M*3+1] slab staged with coalesced loads by the whole block.
   // TMA == true : [kPreThreads][bulk_row_floats(M*3)] rows, each fetched by its own thread with one
   //               cp.async.bulk AFTER the cull tests (culled Gaussians cost no SH traffic) and
@@ -311,7 +311,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     my_rect = pack_rect(rmin, rmax);
     if (tile_count != nullptr) {  // tile-local binning: per-tile entry counters (fire-and-forget reds)
       for (uint32_t y = rmin.y; y < rmax.y; ++y)
-        for (uint32_t x = rmin.x; x < rmax.x; ++x) atomicAdd(tile_count + y * (uint32_t)grid_x + x, 1u);
+        for (uint32_t x = rmin.x; x < rmax.x; ++x) atomicAdd(tile_count + (y * (uint32_t)grid_x + x) * cs, 1u);
     }
     rec[3 * (size_t)idx + 0] = make_float4(pix.x, pix.y, conic.x, conic.y);
     rec[3 * (size_t)idx + 1] = make_float4(conic.z, opacity, power_cut, depth);
@@ -382,7 +382,8 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,        \
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,  \
       cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,        \
-      g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0)
+      g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0,            \
+      (uint32_t)cnt_stride())
   if (tma) {
     if (M == 16) { GSR_PRE_FWD(16, true); } else { GSR_PRE_FWD(4, true); }
   } else {

@@ -26,8 +26,11 @@ namespace gsr {
 namespace {
 
 constexpr int kRedVals = 14;    // accumulator slots reduced per (warp, Gaussian) hit
-constexpr int kRedStride = 36;  // floats per slot row in shared memory (144 B: 16-byte aligned rows
-                                // whose bank offsets rotate by 4, conflict-free per quarter warp)
+// Reduction scratch layout: s_red[slot][warp * 32 + lane] with rows of (32 * warps + 4) floats — the
+// store address is a constant plus 4 * threadIdx.x (cheap to rematerialise, conflict-free), and the
+// row stride is 16 bytes modulo 128, so the 4 x LDS.128 of the reducing lanes (lane -> slot lane >> 1,
+// half lane & 1) are conflict-free per quarter warp as well.
+__host__ __device__ constexpr int red_row(int warps) { return 32 * warps + 4; }
 
 // Reduced slot sets: all 14 accumulator slots, or — for -light's tracking mode (map_off: only the
 // pose gradient is wanted) — just the three the pose contraction reads.
@@ -107,13 +110,11 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   const float* __restrict__ dL_dmedians,  // light
                   const float* __restrict__ dL_dvars,     // light: depth_var, full: uncertainty
                   float* __restrict__ acc) {
-  __shared__ float4 s_r0[kTileThreads];
-  __shared__ float4 s_r1[kTileThreads];
-  __shared__ float4 s_r2[kTileThreads];
+  __shared__ float4 s_rec[3][kTileThreads];
   __shared__ int s_id[kTileThreads];
   __shared__ unsigned short s_mask[kTileThreads];
   __shared__ unsigned char s_list[kTileThreads / 16][kTileThreads];
-  __shared__ __align__(16) float s_red[kTileThreads / 32][kRedVals * kRedStride];
+  __shared__ __align__(16) float s_red[kRedVals][red_row(kTileThreads / 32)];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -155,8 +156,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
   bool mid_once = true;
-  const unsigned red_st = smem_u32(&s_red[warp][lane]);
-  const unsigned red_ld = smem_u32(&s_red[warp][(lane >> 1) * kRedStride + (lane & 1) * 16]);
+  const unsigned red_st = smem_u32(&s_red[0][tid]);
+  const unsigned red_ld = smem_u32(&s_red[(lane >> 1) % kRedVals][(tid & ~31) + (lane & 1) * 16]);
   const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
 
   for (int i = 0; i < rounds; ++i) {
@@ -168,9 +169,9 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       s_id[tid] = id;
       const float4* r = rec + 3 * (size_t)id;
       const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1);
-      s_r0[tid] = q0;
-      s_r1[tid] = q1;
-      s_r2[tid] = __ldg(r + 2);
+      s_rec[0][tid] = q0;
+      s_rec[1][tid] = q1;
+      s_rec[2][tid] = __ldg(r + 2);
       my_mask = block_mask16(q0, q1, tile_x0, tile_y0);
     }
     s_mask[tid] = (unsigned short)my_mask;
@@ -201,8 +202,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       const bool active = k < cnt;
       const int j = active ? (int)my_list[k] : 0;
       const int pos = walk - (i * kTileThreads + j) - 1;  // 0-based list position
-      const float4 r0 = s_r0[j];
-      const float4 r1 = s_r1[j];
+      const float4 r0 = s_rec[0][j];
+      const float4 r1 = s_rec[1][j];
       const float dx = GSR_SUB(r0.x, pixfx), dy = GSR_SUB(r0.y, pixfy);
       const float power = pair_power(r0.z, r0.w, r1.x, dx, dy);
       bool valid = active && (pos < last_contributor) && !(power > 0.0f) && !(power < r1.z);
@@ -222,7 +223,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 #pragma unroll
       for (int q = 0; q < kRedVals; ++q) v[q] = 0.f;
       if (valid) {
-        const float4 r2 = s_r2[j];
+        const float4 r2 = s_rec[2][j];
         const float c_d = r1.w;
         const float inv = fast_rcp(1.f - alpha);   // 1 - alpha >= 0.01
         T = T * inv;
@@ -285,7 +286,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       // half a row (4 x LDS.128), pairs combine with one shuffle, 14 lanes issue one coalesced red
       using RS = RedSet<VARIANT, POSE_ONLY>;
 #pragma unroll
-      for (int q = 0; q < RS::N; ++q) sts_f32(red_st + q * (kRedStride * 4), v[RS::slot(q)]);
+      for (int q = 0; q < RS::N; ++q) sts_f32(red_st + q * (red_row(kTileThreads / 32) * 4), v[RS::slot(q)]);
       __syncwarp();
       float sum = 0.f;
       if (lane < 2 * RS::N) {
@@ -354,12 +355,11 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
                    float* __restrict__ acc) {
   // staged entry, duplicated into pairs: q0 = (xg, pc | yg, yg)  q1 = (A, A | -B, -B)
   //   q2 = (C, C | o, o)  q3 = (depth, depth | r, r)  q4 = (g, g | b, b)
-  __shared__ ulonglong2 s_q0[kBwd2Batch], s_q1[kBwd2Batch], s_q2[kBwd2Batch], s_q3[kBwd2Batch],
-      s_q4[kBwd2Batch];
+  __shared__ ulonglong2 s_q[5][kBwd2Batch];  // one array: an entry's five vectors are constant offsets apart
   __shared__ int s_id[kBwd2Batch];
   __shared__ unsigned char s_mask[kBwd2Batch];
   __shared__ unsigned char s_list[kBwd2Warps][kBwd2Batch];
-  __shared__ __align__(16) float s_red[kBwd2Warps][kRedVals * kRedStride];
+  __shared__ __align__(16) float s_red[kRedVals][red_row(kBwd2Warps)];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -409,8 +409,8 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   f2 T2 = Tf2;
   f2 Bc0 = 0ull, Bc1 = 0ull, Bc2 = 0ull, Bd = 0ull, Bv = 0ull;  // colour / depth / var "behind" the entry
   bool mid_a = true, mid_b = true;
-  const unsigned red_st = smem_u32(&s_red[warp][lane]);
-  const unsigned red_ld = smem_u32(&s_red[warp][(lane >> 1) * kRedStride + (lane & 1) * 16]);
+  const unsigned red_st = smem_u32(&s_red[0][tid]);
+  const unsigned red_ld = smem_u32(&s_red[(lane >> 1) % kRedVals][(tid & ~31) + (lane & 1) * 16]);
 
   for (int i = 0; i < rounds; ++i) {
     __syncthreads();
@@ -422,11 +422,11 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       const float4* r = rec + 3 * (size_t)id;
       const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
       my_mask = block_mask4(q0, q1, tile_x0, tile_y0);
-      s_q0[tid] = make_ulonglong2(f2_pack(q0.x, q1.z), f2_pack(q0.y, q0.y));
-      s_q1[tid] = make_ulonglong2(f2_pack(q0.z, q0.z), f2_pack(-q0.w, -q0.w));
-      s_q2[tid] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q1.y));
-      s_q3[tid] = make_ulonglong2(f2_pack(q1.w, q1.w), f2_pack(q2.x, q2.x));
-      s_q4[tid] = make_ulonglong2(f2_pack(q2.y, q2.y), f2_pack(q2.z, q2.z));
+      s_q[0][tid] = make_ulonglong2(f2_pack(q0.x, q1.z), f2_pack(q0.y, q0.y));
+      s_q[1][tid] = make_ulonglong2(f2_pack(q0.z, q0.z), f2_pack(-q0.w, -q0.w));
+      s_q[2][tid] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q1.y));
+      s_q[3][tid] = make_ulonglong2(f2_pack(q1.w, q1.w), f2_pack(q2.x, q2.x));
+      s_q[4][tid] = make_ulonglong2(f2_pack(q2.y, q2.y), f2_pack(q2.z, q2.z));
     }
     s_mask[tid] = (unsigned char)my_mask;
     __syncthreads();
@@ -447,7 +447,8 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
     for (int k = 0; k < cnt; ++k) {
       const int j = s_list[warp][k];
       const int pos = walk - (i * kBwd2Batch + j) - 1;  // 0-based list position
-      const ulonglong2 e0 = s_q0[j], e1 = s_q1[j], e2 = s_q2[j];
+      const ulonglong2* eq = &s_q[0][j];
+      const ulonglong2 e0 = eq[0], e1 = eq[kBwd2Batch], e2 = eq[2 * kBwd2Batch];
       const float dx = GSR_SUB(f2_lo(e0.x), pxf);
       const float pc = f2_hi(e0.x);
       const f2 dx2 = f2_pack(dx, dx);
@@ -472,7 +473,7 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       if (!vb) { Gb = 0.f; al_b = 0.f; }
       const f2 G2 = f2_pack(Ga, Gb), alpha2 = f2_pack(al_a, al_b);
 
-      const ulonglong2 e3 = s_q3[j], e4 = s_q4[j];
+      const ulonglong2 e3 = eq[3 * kBwd2Batch], e4 = eq[4 * kBwd2Batch];
       const f2 om2 = f2_fma(alpha2, mone2, one2);  // 1 - alpha (>= 0.01)
       const f2 inv2 = f2_pack(fast_rcp(f2_lo(om2)), fast_rcp(f2_hi(om2)));
       T2 = f2_mul(T2, inv2);
@@ -535,7 +536,7 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       using RS = RedSet<VARIANT, POSE_ONLY>;
 #pragma unroll
       for (int qn = 0; qn < RS::N; ++qn)
-        sts_f32(red_st + qn * (kRedStride * 4), f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]));
+        sts_f32(red_st + qn * (red_row(kBwd2Warps) * 4), f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]));
       __syncwarp();
       float sum = 0.f;
       if (lane < 2 * RS::N) {

@@ -36,9 +36,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
                   uint32_t* __restrict__ first_contrib, uint32_t* __restrict__ tile_last,
                   uint32_t* __restrict__ related_counter, FusedLoss fl) {
-  __shared__ float4 s_r0[kTileThreads];
-  __shared__ float4 s_r1[kTileThreads];
-  __shared__ float4 s_r2[kTileThreads];
+  __shared__ float4 s_rec[3][kTileThreads];  // one array: the three rows of an entry are a constant offset apart
   __shared__ int s_id[kTileThreads];
   __shared__ unsigned short s_mask[kTileThreads];                      // sub-block mask per entry
   __shared__ unsigned char s_list[kTileThreads / 16][kTileThreads];    // per-half-warp compacted entries
@@ -64,7 +62,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
   bool done = !inside;
   float T = 1.0f;
-  uint32_t last_contributor = 0, first = 0, valid = 0;
+  uint32_t last_contributor = 0, first = 0xFFFFFFFFu, valid = 0;
   const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, Wsum = 0.f, Dmed = 0.f;
   float gt = 0.f;
@@ -79,9 +77,9 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       s_id[tid] = id;
       const float4* r = rec + 3 * (size_t)id;
       const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1);
-      s_r0[tid] = q0;
-      s_r1[tid] = q1;
-      s_r2[tid] = __ldg(r + 2);
+      s_rec[0][tid] = q0;
+      s_rec[1][tid] = q1;
+      s_rec[2][tid] = __ldg(r + 2);
       my_mask = block_mask16(q0, q1, tile_x0, tile_y0);
     }
     s_mask[tid] = (unsigned short)my_mask;
@@ -110,11 +108,13 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       cnt = half ? cnt_hi : cnt_lo;
     }
     const unsigned char* my_list = s_list[2 * warp + half];
-    for (int k = 0; !done && k < cnt; ++k) {
+    if (done) cnt = 0;
+    const uint32_t contrib_base = (uint32_t)(i * kTileThreads + 1);
+    for (int k = 0; k < cnt; ++k) {
       const int j = my_list[k];
-      const uint32_t contributor = (uint32_t)(i * kTileThreads + j + 1);  // 1-based list position
-      const float4 r0 = s_r0[j];
-      const float4 r1 = s_r1[j];
+      const uint32_t contributor = contrib_base + (uint32_t)j;  // 1-based list position
+      const float4 r0 = s_rec[0][j];
+      const float4 r1 = s_rec[1][j];
       const float dx = GSR_SUB(r0.x, pixfx), dy = GSR_SUB(r0.y, pixfy);
       const float power = pair_power(r0.z, r0.w, r1.x, dx, dy);
       if (power > 0.0f) continue;
@@ -126,9 +126,9 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         const float test_T = GSR_MUL(T, GSR_SUB(1.f, alpha));
         if (test_T < kTmin) {
           done = true;
-          continue;
+          break;
         }
-        const float4 r2 = s_r2[j];
+        const float4 r2 = s_rec[2][j];
         const float depth = r1.w;
         C0 = GSR_FMA(T, GSR_MUL(alpha, r2.x), C0);
         C1 = GSR_FMA(T, GSR_MUL(alpha, r2.y), C1);
@@ -147,18 +147,21 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         T = test_T;
         last_contributor = contributor;
       } else {
-        const float4 r2 = s_r2[j];
+        const float4 r2 = s_rec[2][j];
         const float depth = r1.w;
         C0 = GSR_FMA(T, GSR_MUL(alpha, r2.x), C0);
         C1 = GSR_FMA(T, GSR_MUL(alpha, r2.y), C1);
         C2 = GSR_FMA(T, GSR_MUL(alpha, r2.z), C2);
         D = GSR_FMA(T, GSR_MUL(alpha, depth), D);
         Wsum = GSR_FMA(T, alpha, Wsum);
-        if (valid == 0) first = contributor;
+        first = min(first, contributor);  // entries come in increasing position order
         ++valid;
         T = GSR_MUL(T, GSR_SUB(1.f, alpha));
         last_contributor = contributor;
-        if (T < kTmin) done = true;
+        if (T < kTmin) {
+          done = true;
+          break;
+        }
       }
     }
   }
@@ -182,7 +185,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       }
     } else {
       final_T[pix_id] = T;
-      first_contrib[pix_id] = first;
+      first_contrib[pix_id] = (first == 0xFFFFFFFFu) ? 0u : first;
     }
     if (LOSS) {
       // fused masked-L1 loss and its cotangents (tracker.cu): the images need not leave the chip

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kUpdThreads)
 track_update_kernel(int nblocks, const float* __restrict__ partials, int tiles,
                     const float* __restrict__ loss_partials, PoseState* ps,
                     const float* __restrict__ persp, float* view, float* proj, float* campos,
-                    float* loss_hist, uint32_t* tile_count, uint32_t* counters, UpdateParams up) {
+                    float* loss_hist, uint32_t* tile_count, uint32_t* counters, UpdateParams up, int cs) {
   __shared__ float s_g[12];
   __shared__ float s_l[4];
   __shared__ PoseState s_ps;   // the pose state travels through shared memory: one coalesced load /
@@ -190,7 +190,7 @@ track_update_kernel(int nblocks, const float* __restrict__ partials, int tiles,
     write_camera(p, p + 4, s_persp, view, proj, campos);
     counters[0] = 0u; counters[1] = 0u; counters[2] = 0u;  // [3] (overflow flag) is sticky
   }
-  for (int i = tid; i < tiles; i += kUpdThreads) tile_count[i] = 0u;
+  for (int i = tid; i < tiles * cs; i += kUpdThreads) tile_count[i] = 0u;
   __syncthreads();
   if (tid < kPsWords) reinterpret_cast<uint32_t*>(ps)[tid] = reinterpret_cast<const uint32_t*>(&s_ps)[tid];
 }
@@ -299,7 +299,7 @@ int enqueue_iteration(gsr_tracker* t, const gsr_track_params& prm, int packed_en
   track_update_kernel<<<1, kUpdThreads, 0, s>>>(nblocks, partials, t->camera.grid_x * t->camera.grid_y,
                                                 t->loss_partials, t->ps, persp, t->cam, t->cam + 16,
                                                 t->cam + 32, t->loss_hist, t->img.tile_count,
-                                                t->g.counters, up);
+                                                t->g.counters, up, cnt_stride());
   GSR_LAUNCH_OK(false, s);
   return GSR_OK;
 }
@@ -352,7 +352,7 @@ gsr_tracker* gsr_tracker_create(int P, int D, int M, int width, int height, floa
   cudaMemcpyAsync(t->cam + 36, perspec_matrix_host, sizeof(float) * 16, cudaMemcpyHostToDevice, t->stream);
   cudaMemsetAsync(t->ps, 0, sizeof(PoseState), t->stream);
   cudaMemsetAsync(t->g.counters, 0, 8 * sizeof(uint32_t), t->stream);
-  cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, t->stream);
+  cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles * kCntStrideMax, t->stream);
   if (cudaStreamSynchronize(t->stream) != cudaSuccess) {
     set_error("gsr_tracker_create: initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
     tracker_free(t);
@@ -419,7 +419,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
   uint32_t h[4] = {0, 0, 0, 0};
   {
     GSR_CUDA_OK(cudaMemsetAsync(t->g.counters, 0, 8 * sizeof(uint32_t), s));
-    GSR_CUDA_OK(cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, s));
+    GSR_CUDA_OK(cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles * kCntStrideMax, s));
     int rc = enqueue_preprocess(t);
     if (rc != GSR_OK) return rc;
     rc = probe_tile_counts(t->camera, t->g, t->img, s);
@@ -445,7 +445,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
     memcpy(key.ptrs, ptrs, sizeof(ptrs));
     key.scale_modifier = t->scale_modifier; key.params = *params;
     key.capacity = t->capacity; key.longest_cap = t->longest_cap;
-    key.opts[0] = options().tight_tiles; key.opts[1] = options().bwd_packed;
+    key.opts[0] = options().tight_tiles; key.opts[1] = options().bwd_packed + 16 * cnt_stride();
     key.packed = (double)packed_entries >= 1.6 * (double)t->P;
     if (!t->key_valid || memcmp(&key, &t->key, sizeof(key)) != 0 || !t->exec) {
       if (t->exec) { cudaGraphExecDestroy(t->exec); t->exec = nullptr; }
@@ -470,7 +470,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
     init_camera_kernel<<<1, 32, 0, s>>>(t->ps, t->cam + 36, t->cam, t->cam + 16, t->cam + 32);
     GSR_LAUNCH_OK(false, s);
     GSR_CUDA_OK(cudaMemsetAsync(t->g.counters, 0, 8 * sizeof(uint32_t), s));
-    GSR_CUDA_OK(cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, s));
+    GSR_CUDA_OK(cudaMemsetAsync(t->img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles * kCntStrideMax, s));
     GSR_CUDA_OK(cudaMemsetAsync(t->scratch, 0, (size_t)t->P * kAccStride * sizeof(float), s));
     for (int i = 0; i < iterations; ++i) GSR_CUDA_OK(cudaGraphLaunch(t->exec, s));
     uint32_t flag[4] = {0, 0, 0, 0};

@@ -92,6 +92,9 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *   "bulk_sh"       1 (default): the per-Gaussian kernels move SH rows (M = 16 or 4, 16-byte aligned)
  *                   between global and shared memory with cp.async.bulk (TMA), one row per thread and
  *                   only for Gaussians that survive culling; 0: block-wide coalesced staging.
+ *   "cnt_stride"    spacing (in 32-bit words, 1..32, default 8 = one per 32-byte sector) of the per-tile
+ *                   entry counters / scatter cursors: neighbouring tiles' atomics no longer serialise on
+ *                   one cache line (measured: preprocess_fwd 0.078 -> 0.069 ms, scatter 0.059 -> 0.042 ms).
  *   "track_headroom_pct" head room (percent, default 50) of the tracker's binning buffer over the
  *                   counts of its probing forward; negative values force the overflow / retry path
  *                   (test hook).
