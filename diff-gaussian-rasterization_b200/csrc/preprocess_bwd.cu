@@ -40,8 +40,11 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
 // TMA == true (MT = 16 / 4 on 16-byte aligned tensors): every thread moves its own Gaussian's SH row
 // with cp.async.bulk — in only if the Gaussian is visible, awaited right before the SH backward —
 // and its dL/dSH row back out with a bulk store; no block-wide staging loops, no barriers.
-template <int VARIANT, int MT, bool TMA>  // MT: compile-time SH coefficient count (16/9/4/1) or 0 = runtime M
-__global__ void __launch_bounds__(kBwdThreads)
+// MINB (min CTAs per SM) is 5 for the M = 16 bulk-copy variant: 96 registers, measured best (4 CTAs at
+// 113-127 registers: +10 % time, 6 CTAs with spills: +3 %); a dense-row variant with ONE bulk store per
+// warp instead of one per thread was 8 % slower (4-way bank conflicts on the row accesses).
+template <int VARIANT, int MT, bool TMA, int MINB = 1>  // MT: compile-time SH coefficient count (16/9/4/1) or 0 = runtime M
+__global__ void __launch_bounds__(kBwdThreads, MINB)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const int* __restrict__ radii, const float* __restrict__ shs,
                       const unsigned char* __restrict__ clamped, const float* __restrict__ scales,
@@ -549,9 +552,9 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   }
   {
 #define GSR_PRE_BWD(V, MT, TMA)                                                                  \
-  cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, \
-                       cudaSharedmemCarveoutMaxShared);                                          \
-  preprocess_bwd_kernel<V, MT, TMA><<<blocks, kBwdThreads, smem, stream>>>(                      \
+  cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1>,         \
+                       cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+  preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1><<<blocks, kBwdThreads, smem, stream>>>( \
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
       g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr)

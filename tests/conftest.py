@@ -32,7 +32,16 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def built():
-    """Build (incrementally) the core library, torch shims and the oracle once per session."""
+    """Build (incrementally) the core library, torch shims and the oracle once per session.
+    GSR_TEST_OPTS="key=value,..." applies library options (gsr_set_option) for the whole session, so
+    the parity suite can be run against a non-default kernel variant."""
     import __graft_entry__ as ge
     ge.build_product()
+    opts = os.environ.get("GSR_TEST_OPTS", "")
+    if opts:
+        import ctypes
+        lib = ctypes.CDLL(ge.core_library_path())
+        for kv in opts.split(","):
+            k, v = kv.split("=")
+            assert lib.gsr_set_option(k.encode(), int(v)) >= 0, "unknown option " + k
     return ge
