@@ -513,12 +513,31 @@ def main():
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top, {}).get(a.config)
             except Exception:
                 pass
+            inst = None
+            try:
+                inst = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(
+                    "inst_executed", {}).get(top, {}).get(a.config)
+            except Exception:
+                pass
             out["roofline"] = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                                "algorithmic_bytes": nbytes, "kernel_ms": dur_ms,
                                "share_of_step": stage_ms[top] / ms_per_step,
                                "note": "blend kernels are FP32-issue / MUFU / L2-atomic bound, not HBM bound "
                                        "(DESIGN.md); the HBM fraction is reported because the metric asks for it"}
+            if inst and clk and clk.get("sm_mhz"):
+                # the bound that actually limits the blend kernels: warp-instruction issue slots
+                # (148 SMs x 4 schedulers x SM clock); instruction count from the committed ncu capture
+                peak_ips = 148 * 4 * float(clk["sm_mhz"]) * 1e6
+                out["roofline"]["issue"] = {"warp_instructions": inst, "peak_per_s": peak_ips,
+                                            "achieved_per_s": inst / (dur_ms * 1e-3),
+                                            "frac": inst / (dur_ms * 1e-3) / peak_ips}
+            # every stage against the HBM roofline (algorithmic bytes / measured stage time)
+            out["roofline_by_stage"] = {
+                k: {"ms": stage_ms[k], "algorithmic_bytes": b, "achieved_gbs": b / (stage_ms[k] * 1e-3) / 1e9,
+                    "frac": b / (stage_ms[k] * 1e-3) / 1e9 / peak}
+                for k in stage_ms
+                for b in [stage_bytes(k, P, num_rendered or 0, W * H, tiles, 16, a.variant, sort_bits)] if b}
             frame_bytes = sum(stage_bytes(k, P, num_rendered or 0, W * H, tiles, 16, a.variant, sort_bits) or 0
                               for k in ("preprocess_fwd", "scan", "emit_keys", "radix_sort", "tile_ranges",
                                         "render_fwd", "render_bwd", "preprocess_bwd"))

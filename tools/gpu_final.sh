@@ -13,7 +13,7 @@ python bench.py --steps 30 --warmup 5 > $O/bench.json 2> $O/bench.err; echo "ben
 python bench.py --steps 30 --warmup 5 --variant light --cpu-frames 0 > $O/bench_light.json 2>> $O/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/launches_C3.csv \
     python bench.py --steps 2 --warmup 3 --cpu-frames 0 > $O/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'render_|preprocess_bwd' -s 9 -c 3 -f -o $O/prof_C3 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'render_|preprocess_' -s 14 -c 4 -f -o $O/prof_C3 \
     python bench.py --steps 2 --warmup 3 --cpu-frames 0 --no-stage-timing > $O/ncu_full_C3.log 2>&1; echo "ncu full rc=$?"
 ncu -i $O/prof_C3.ncu-rep --page raw --csv > $O/prof_C3_raw.csv 2>/dev/null
 ncu -i $O/prof_C3.ncu-rep --page source --csv > $O/prof_C3_src.csv 2>/dev/null
@@ -23,7 +23,7 @@ timeout 600 ncu --graph-profiling node --metrics gpu__time_duration.sum --clock-
 bash tools/gpu_configs.sh > $O/configs.txt 2>&1; cp -r gpurun_out/configs $O/ 2>/dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_C4.csv \
     python bench.py --config C4 --steps 2 --warmup 3 --cpu-frames 0 > $O/bench_C4_under_ncu.log 2>&1; echo "ncu C4 list rc=$?"
-timeout 900 ncu --set full --clock-control none -k regex:'render_|preprocess_' -s 12 -c 4 -f -o $O/prof_C4 \
+timeout 900 ncu --set full --clock-control none -k regex:'render_|preprocess_' -s 14 -c 4 -f -o $O/prof_C4 \
     python bench.py --config C4 --steps 2 --warmup 3 --cpu-frames 0 --no-stage-timing > $O/ncu_full_C4.log 2>&1; echo "ncu C4 full rc=$?"
 ncu -i $O/prof_C4.ncu-rep --page raw --csv > $O/prof_C4_raw.csv 2>/dev/null
 rm -f $O/prof_C4.ncu-rep
