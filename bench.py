@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--no-stage-timing", action="store_true")
     ap.add_argument("--track-off", action="store_true", help="-light only: mapping mode (no pose gradient)")
     ap.add_argument("--map-off", action="store_true", help="-light only: tracking mode (pose gradient only)")
-    ap.add_argument("--dp-mode", default="factorized_sh", choices=["allreduce", "factorized_sh"],
+    ap.add_argument("--dp-mode", default="factorized_sh", choices=["allreduce", "factorized_sh", "nvls"],
                     help="gradient exchange at N > 1 (diff-gaussian-rasterization_b200/dp.py)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (gsr_set_option)")
     a = ap.parse_args()
@@ -377,7 +377,8 @@ def main():
         dp_mode = a.dp_mode if a.impl == "b200" else "allreduce"   # the reference has no masked colour output
         reducer = dp.SceneGradReducer(shapes, device, mode=dp_mode, means3D=frame.params["means3D"], sh_degree=3)
         zero_copy = reducer.attach(mod)   # B200 arm: backward writes into the flat buffer directly
-        log("rank %d: exchange mode %s, gradient arena attached: %s" % (rank, dp_mode, zero_copy))
+        log("rank %d: exchange mode %s (requested %s), gradient arena attached: %s %s" % (
+            rank, reducer.mode, dp_mode, zero_copy, getattr(reducer, "nvls_note", None) or ""))
 
     lib = None
     if a.impl == "b200":

@@ -80,6 +80,7 @@ RasterizeGaussiansBackwardCUDA(
 // instead of dL_dsh (whose returned tensor is undefined / None); the summed dL_dsh of all views is
 // rebuilt with shGradFromViews after an all-gather of the first 3P + 4 floats.
 void setGradArena(const torch::Tensor& arena, bool factorized_sh);
+void setGradArenaNvls(const torch::Tensor& arena, int64_t mc_ptr, int64_t rank, int64_t world);
 void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom,
                      const torch::Tensor& max_radii2D);
 

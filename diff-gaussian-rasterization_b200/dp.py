@@ -12,6 +12,13 @@ reduced.  Two exchange modes:
       so ranks all-gather 3 floats per Gaussian (+ the camera position) and all-reduce only the other
       11 floats; every rank rebuilds the summed dL/dsh locally (`_C.sh_grad_from_views`).  Same result
       up to summation order, 14 instead of 59 floats per Gaussian on the wire.
+  "nvls"  the factorized exchange done INSIDE the backward's per-Gaussian kernel over NVSwitch
+      multicast: the gradient arena is symmetric memory (torch.distributed._symmetric_memory), the kernel
+      adds the 11 reduced floats of every visible Gaussian with multimem.red to the arena's multicast
+      alias (the switch reduces; every rank's replica ends up with the sum) and multicast-stores the
+      masked colour gradient + camera position into its slot of every replica.  No collective call: what
+      is left per step is a memset of the other buffer of the double-buffered arena, one device-side
+      barrier and the local SH rebuild.  Falls back to "factorized_sh" when multicast is unavailable.
 
 With `attach()` the backward of the B200-native packages writes its gradients straight into the
 flat buffer (no packing copy).  The collectives run on a side stream; `wait()` makes the reduced
@@ -74,8 +81,14 @@ class SceneGradReducer:
                  sh_degree=3):
         """shapes: mapping name -> shape for the entries of PARAM_ORDER that exist.
         mode "factorized_sh" additionally needs the (replicated) means3D parameter tensor."""
-        assert mode in ("allreduce", "factorized_sh")
+        assert mode in ("allreduce", "factorized_sh", "nvls")
         self.group, self.average, self.mode = group, average, mode
+        self.nvls = None
+        if mode == "nvls":
+            self.mode = mode = "factorized_sh"   # layout and SH rebuild are those of the factorized exchange
+            self._nvls_requested = True
+        else:
+            self._nvls_requested = False
         self.is_cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
         self._work, self._done, self._attached = None, None, None
@@ -103,6 +116,62 @@ class SceneGradReducer:
             self.sh_sum = None
             self.gathered = None
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        if self._nvls_requested:
+            self._setup_nvls(device)
+
+    # ---- NVLS (in-switch) exchange -----------------------------------------------------------------
+    def _setup_nvls(self, device):
+        """Allocate the double-buffered symmetric arena; on any failure stay on the NCCL path."""
+        self.nvls_note = None
+        try:
+            if not (self.is_cuda and dist.is_available() and dist.is_initialized()) or self._world() < 2:
+                raise RuntimeError("needs CUDA and an initialised process group with world_size > 1")
+            import torch.distributed._symmetric_memory as symm_mem
+            world, rank = self._world(), dist.get_rank(self.group)
+            group = self.group if self.group is not None else dist.group.WORLD
+            numel = world * self.head + 11 * self.P
+            arenas, handles = [], []
+            for _ in range(2):
+                t = symm_mem.empty(numel, dtype=torch.float32, device=torch.device(device))
+                h = symm_mem.rendezvous(t, group)
+                if not int(h.multicast_ptr):
+                    raise RuntimeError("no multicast support on this system")
+                t.zero_()
+                arenas.append(t)
+                handles.append(h)
+            torch.cuda.synchronize(device)
+            handles[0].barrier(channel=0, timeout_ms=30000)
+            torch.cuda.synchronize(device)
+            off = world * self.head
+            red = OrderedDict()
+            for name, n, shape in (("means3D", 3 * self.P, (self.P, 3)), ("opacities", self.P, (self.P, 1)),
+                                   ("scales", 3 * self.P, (self.P, 3)), ("rotations", 4 * self.P, (self.P, 4))):
+                red[name] = (off, n, shape)
+                off += n
+            self.nvls = dict(arenas=arenas, handles=handles, cur=0, done=None, world=world, rank=rank, slices=red)
+            self.mode = "nvls"
+        except Exception as e:  # noqa: BLE001 - any failure means: use the NCCL exchange
+            self.nvls = None
+            self.nvls_note = "nvls unavailable (%s: %s); using factorized_sh" % (type(e).__name__, e)
+
+    def _nvls_register(self):
+        n = self.nvls
+        self._attached._C.set_grad_arena_nvls(n["arenas"][n["cur"]], int(n["handles"][n["cur"]].multicast_ptr),
+                                              n["rank"], n["world"])
+
+    def _nvls_exchange(self):
+        """Runs on the side stream after the backward: zero the other buffer, barrier, rebuild dL/dsh."""
+        n = self.nvls
+        cur, nxt = n["cur"], 1 - n["cur"]
+        n["arenas"][nxt].zero_()
+        n["handles"][cur].barrier(channel=0, timeout_ms=30000)
+        gathered = n["arenas"][cur][:n["world"] * self.head].view(n["world"], self.head)
+        self.sh_sum = self._attached._C.sh_grad_from_views(self.means3D.detach(), gathered, self.sh_degree, self.M)
+        if self.average:
+            n["arenas"][cur][n["world"] * self.head:].div_(n["world"])
+            self.sh_sum.div_(n["world"])
+        n["done"] = cur
+        n["cur"] = nxt
 
     # ---- wiring -------------------------------------------------------------------------------
     def attach(self, rasterizer_module):
@@ -111,9 +180,14 @@ class SceneGradReducer:
         Returns False (and changes nothing) for packages without that extension (the reference)."""
         fn = getattr(getattr(rasterizer_module, "_C", None), "set_grad_arena", None)
         if fn is None or not self.is_cuda:
+            if self.mode == "nvls":      # the reference package cannot do it: NCCL exchange instead
+                self.mode, self.nvls = "factorized_sh", None
             return False
-        fn(self.flat, self.mode == "factorized_sh")
         self._attached = rasterizer_module
+        if self.mode == "nvls":
+            self._nvls_register()
+        else:
+            fn(self.flat, self.mode == "factorized_sh")
         return True
 
     def detach(self):
@@ -123,6 +197,12 @@ class SceneGradReducer:
 
     def views(self):
         """Per-parameter reduced gradients (valid after wait())."""
+        if self.mode == "nvls":
+            n = self.nvls
+            buf = n["arenas"][n["done"] if n["done"] is not None else n["cur"]]
+            out = {k: buf[o:o + m].view(shape) for k, (o, m, shape) in n["slices"].items()}
+            out["shs"] = self.sh_sum
+            return out
         out = {k: self.flat[o:o + n].view(shape) for k, (o, n, shape) in self.slices.items()}
         if self.mode == "factorized_sh":
             out["shs"] = self.sh_sum
@@ -137,6 +217,11 @@ class SceneGradReducer:
             self.flat[3 * self.P:3 * self.P + 3].copy_(campos.reshape(-1)[:3])
 
     def _aliases_flat(self, grads):
+        if self.mode == "nvls":
+            n = self.nvls
+            lo = n["arenas"][n["cur"]].data_ptr()
+            return all(grads.get(k) is not None and grads[k].data_ptr() == lo + 4 * o
+                       for k, (o, _m, _s) in n["slices"].items())
         lo = self.flat.data_ptr()
         for k, (o, _n, _shape) in self.slices.items():
             g = grads.get(k)
@@ -180,6 +265,17 @@ class SceneGradReducer:
     def reduce_async(self, grads=None, masked_color=None, campos=None):
         """Pack (unless the gradients already live in the flat buffer, see attach()) and launch the
         exchange.  Returns immediately on CUDA; call wait() before reading views()."""
+        if self.mode == "nvls":
+            if grads is not None and not self._aliases_flat(grads):
+                raise RuntimeError("nvls exchange: the gradients were not produced into the symmetric arena "
+                                   "(attach() the rasterizer package and call wait() after every reduce_async())")
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self._nvls_exchange()
+                self._done = torch.cuda.Event()
+                self._done.record(self.stream)
+            self._nvls_register()   # the next backward writes into the other buffer
+            return
         if grads is not None and not (self._attached is not None and self._aliases_flat(grads)):
             self.pack(grads, masked_color, campos)
         if self.is_cuda:
@@ -199,4 +295,6 @@ class SceneGradReducer:
 
     def bytes_per_step(self):
         """fp32 bytes this rank contributes to the exchange per step."""
+        if self.mode == "nvls":
+            return (14 * self.P + 4) * 4
         return self.numel * 4

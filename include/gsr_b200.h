@@ -131,6 +131,16 @@ typedef struct gsr_backward_extras {
   float* densify_grad_accum;
   float* densify_denom;
   float* max_radii2D;
+  /* In-switch gradient exchange for view-level data parallelism over NVSwitch multicast (NVLS).
+   * mc_delta != 0 says: dL_dmean3D, dL_dopacity, dL_dscale, dL_drot and dL_dcolor_masked point into
+   * THIS rank's replica of a symmetric arena whose multicast alias lies mc_delta bytes further.  The
+   * per-Gaussian backward kernel then does not store those gradients locally but issues, for visible
+   * Gaussians only, multimem.red.add (the four reduced gradients: every rank's replica of a pre-zeroed
+   * arena ends up holding the SUM over ranks) and multimem.st (the masked colour gradient and, if
+   * cam_pos_out != NULL, the camera position — written into this rank's slot of every replica).
+   * The exchange is thereby part of the kernel that produces the gradients: no separate collective. */
+  long long mc_delta;
+  float* cam_pos_out;      /* [3] inside the arena (local address); NULL = not wanted */
 } gsr_backward_extras;
 
 /* ---- light variant ---------------------------------------------------------------------- */
