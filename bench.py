@@ -459,6 +459,10 @@ def main():
     e2e_ms = timed_region(torch, dist, step_e2e, a.steps, world)
     clk = clocks.stop() if rank == 0 else None
 
+    if reducer is not None and getattr(reducer, "nvls", None) and rank == 0:
+        tt = reducer.nvls_timing()
+        if tt:
+            log("nvls exchange phases (ms): barrier A %.3f, slice all-reduce %.3f, SH rebuild (P2P) %.3f, barrier B %.3f" % tuple(tt))
     if world > 1:
         dist.barrier()
     if rank != 0:

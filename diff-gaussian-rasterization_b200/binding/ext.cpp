@@ -11,9 +11,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // extension (not in the reference): flat scene-gradient arena for view-level data parallelism
   m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false);
   m.def("sh_grad_from_views", &shGradFromViews);
-  // extension: in-switch (NVLS multicast) gradient exchange, see dp.py mode "nvls"
-  m.def("set_grad_arena_nvls", &setGradArenaNvls, pybind11::arg("arena"), pybind11::arg("mc_ptr"),
-        pybind11::arg("rank"), pybind11::arg("world"));
+  // extensions for the NVLS exchange of dp.py (mode "nvls"): P2P-reading SH rebuild, in-switch slice all-reduce
+  m.def("sh_grad_from_view_ptrs", &shGradFromViewPtrs);
+  m.def("nvls_allreduce_slice", &nvlsAllreduceSlice);
   // extension (not in the reference): in-kernel densification statistics
   m.def("set_densify_stats", &setDensifyStats, pybind11::arg("grad_accum"), pybind11::arg("denom"),
         pybind11::arg("max_radii2D"));

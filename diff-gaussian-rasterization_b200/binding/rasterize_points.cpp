@@ -50,16 +50,11 @@ torch::Tensor scratch_for(int P, const torch::TensorOptions& fopts) {
 torch::Tensor g_grad_arena;  // see setGradArena
 torch::Tensor g_densify_accum, g_densify_denom, g_max_radii;  // see setDensifyStats
 bool g_arena_factorized = false;
-// NVLS arena (setGradArenaNvls): multicast alias, this rank's slot and the number of ranks
-int64_t g_arena_mc_ptr = 0;
-int g_arena_rank = 0, g_arena_world = 0;
 
 struct SceneGrads {
   torch::Tensor means3D, sh, opacity, scales, rotations;
   torch::Tensor masked_color;  // factorized arena only
   bool factorized = false;
-  long long mc_delta = 0;      // NVLS arena only
-  float* cam_pos_out = nullptr;
 };
 
 // densification accumulators registered with setDensifyStats, when they fit this scene
@@ -78,26 +73,6 @@ SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torc
   const bool arena_ok = g_grad_arena.defined() && g_grad_arena.device() == like.device() &&
                         g_grad_arena.scalar_type() == torch::kFloat32 && g_grad_arena.is_contiguous() &&
                         P > 0 && P % 4 == 0;
-  if (arena_ok && g_arena_mc_ptr != 0 && M > 0 &&
-      g_grad_arena.numel() == (int64_t)g_arena_world * (3 * (int64_t)P + 4) + 11 * (int64_t)P) {
-    // NVLS layout: [ world x (masked colour 3P | campos 3 | pad) ][ means3D 3P | opacity P | scales 3P | rot 4P ]
-    const int64_t head = 3 * (int64_t)P + 4;
-    int64_t off = (int64_t)g_arena_world * head;
-    auto take = [&](int64_t n, std::vector<int64_t> shape) {
-      torch::Tensor t = g_grad_arena.narrow(0, off, n).view(shape);
-      off += n;
-      return t;
-    };
-    g.factorized = true;
-    g.masked_color = g_grad_arena.narrow(0, (int64_t)g_arena_rank * head, (int64_t)P * 3).view({P, 3});
-    g.cam_pos_out = g_grad_arena.data_ptr<float>() + (int64_t)g_arena_rank * head + 3 * (int64_t)P;
-    g.mc_delta = (long long)(g_arena_mc_ptr - reinterpret_cast<int64_t>(g_grad_arena.data_ptr()));
-    g.means3D = take((int64_t)P * 3, {P, 3});
-    g.opacity = take((int64_t)P, {P, 1});
-    g.scales = take((int64_t)P * 3, {P, 3});
-    g.rotations = take((int64_t)P * 4, {P, 4});
-    return g;
-  }
   if (arena_ok && g_arena_factorized && M > 0 && g_grad_arena.numel() == (int64_t)P * 14 + 4) {
     int64_t off = 0;
     auto take = [&](int64_t n, std::vector<int64_t> shape) {
@@ -237,17 +212,12 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
-  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr};
+  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr};
   fill_densify(extras, P, means3D);
   if (sg.factorized) {
     extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
     extras.skip_sh_grad = 1;
-    if (sg.mc_delta != 0) {  // NVLS: the kernel multicasts gradients and camera position itself
-      extras.mc_delta = sg.mc_delta;
-      extras.cam_pos_out = sg.cam_pos_out;
-    } else {
-      g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
-    }
+    g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
   }
   torch::Tensor dL_dscales = sg.scales;
   torch::Tensor dL_drotations = sg.rotations;
@@ -369,17 +339,12 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
-  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr};
+  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr};
   fill_densify(extras, P, means3D);
   if (sg.factorized) {
     extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
     extras.skip_sh_grad = 1;
-    if (sg.mc_delta != 0) {  // NVLS: the kernel multicasts gradients and camera position itself
-      extras.mc_delta = sg.mc_delta;
-      extras.cam_pos_out = sg.cam_pos_out;
-    } else {
-      g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
-    }
+    g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
   }
   torch::Tensor dL_dscales = sg.scales;
   torch::Tensor dL_drotations = sg.rotations;
@@ -440,21 +405,7 @@ void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom
   }
 }
 
-// NVLS exchange: `arena` is this rank's replica of a symmetric-memory buffer (pre-zeroed by the
-// caller on every rank), `mc_ptr` its multicast alias (torch symmetric memory: handle.multicast_ptr).
-void setGradArenaNvls(const torch::Tensor& arena, int64_t mc_ptr, int64_t rank, int64_t world) {
-  TORCH_CHECK(arena.is_cuda() && arena.scalar_type() == torch::kFloat32 && arena.is_contiguous() &&
-                  arena.dim() == 1 && mc_ptr != 0 && world > 0 && rank >= 0 && rank < world,
-              "NVLS grad arena: need a contiguous 1-D float32 CUDA tensor, a multicast pointer and a valid rank");
-  g_grad_arena = arena;
-  g_arena_factorized = true;
-  g_arena_mc_ptr = mc_ptr;
-  g_arena_rank = (int)rank;
-  g_arena_world = (int)world;
-}
-
 void setGradArena(const torch::Tensor& arena, bool factorized_sh) {
-  g_arena_mc_ptr = 0;
   g_arena_factorized = factorized_sh;
   if (!arena.defined() || arena.numel() == 0) {
     g_grad_arena = torch::Tensor();
@@ -481,6 +432,34 @@ torch::Tensor shGradFromViews(const torch::Tensor& means3D, const torch::Tensor&
                                         at::cuda::getCurrentCUDAStream().stream());
   check_rc(rc, "gsr_sh_grad_from_views");
   return out;
+}
+
+torch::Tensor shGradFromViewPtrs(const torch::Tensor& means3D, const std::vector<int64_t>& dR_ptrs,
+                                 const std::vector<int64_t>& campos_ptrs, const int degree, const int M) {
+  TORCH_CHECK(means3D.is_cuda(), "sh_grad_from_view_ptrs needs a CUDA tensor");
+  TORCH_CHECK(dR_ptrs.size() == campos_ptrs.size(), "one camera position per view");
+  const c10::cuda::CUDAGuard guard(means3D.device());
+  const auto dev = means3D.device();
+  const int P = means3D.size(0);
+  const auto mu = prep(means3D, dev, "means3D");
+  std::vector<const float*> dr, cp;
+  for (size_t v = 0; v < dR_ptrs.size(); ++v) {
+    dr.push_back(reinterpret_cast<const float*>(dR_ptrs[v]));
+    cp.push_back(reinterpret_cast<const float*>(campos_ptrs[v]));
+  }
+  torch::Tensor out = torch::empty({P, M, 3}, means3D.options().dtype(torch::kFloat32));
+  const int rc = gsr_sh_grad_from_view_ptrs(P, degree, M, fptr(mu), (int)dr.size(), dr.data(), cp.data(),
+                                            out.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream());
+  check_rc(rc, "gsr_sh_grad_from_view_ptrs");
+  return out;
+}
+
+void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t count_floats, int64_t rank,
+                        int64_t world) {
+  const int rc = gsr_nvls_allreduce_slice(reinterpret_cast<float*>(multicast_ptr), (size_t)offset_floats,
+                                          (size_t)count_floats, (int)rank, (int)world,
+                                          at::cuda::getCurrentCUDAStream().stream());
+  check_rc(rc, "gsr_nvls_allreduce_slice");
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,

@@ -80,7 +80,10 @@ RasterizeGaussiansBackwardCUDA(
 // instead of dL_dsh (whose returned tensor is undefined / None); the summed dL_dsh of all views is
 // rebuilt with shGradFromViews after an all-gather of the first 3P + 4 floats.
 void setGradArena(const torch::Tensor& arena, bool factorized_sh);
-void setGradArenaNvls(const torch::Tensor& arena, int64_t mc_ptr, int64_t rank, int64_t world);
+torch::Tensor shGradFromViewPtrs(const torch::Tensor& means3D, const std::vector<int64_t>& dR_ptrs,
+                                 const std::vector<int64_t>& campos_ptrs, const int degree, const int M);
+void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t count_floats, int64_t rank,
+                        int64_t world);
 void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom,
                      const torch::Tensor& max_radii2D);
 

@@ -389,7 +389,7 @@ int gsr_light_backward(
     if (rc != GSR_OK) return rc;
   }
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
-                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr};
   if (extras != nullptr) {
     out.dL_dcolor_masked = extras->dL_dcolor_masked;
     if (extras->skip_sh_grad) out.dL_dsh = nullptr;
@@ -398,8 +398,6 @@ int gsr_light_backward(
       out.densify_denom = extras->densify_denom;
     }
     out.max_radii2D = extras->max_radii2D;
-    out.mc_delta = extras->mc_delta;
-    out.cam_pos_out = extras->cam_pos_out;
   }
   return launch_preprocess_bwd(kLight, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
@@ -444,7 +442,7 @@ int gsr_full_backward(
   rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, false, s);
   if (rc != GSR_OK) return rc;
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
-                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+                   dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr};
   if (extras != nullptr) {
     out.dL_dcolor_masked = extras->dL_dcolor_masked;
     if (extras->skip_sh_grad) out.dL_dsh = nullptr;
@@ -453,8 +451,6 @@ int gsr_full_backward(
       out.densify_denom = extras->densify_denom;
     }
     out.max_radii2D = extras->max_radii2D;
-    out.mc_delta = extras->mc_delta;
-    out.cam_pos_out = extras->cam_pos_out;
   }
   return launch_preprocess_bwd(kFull, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,

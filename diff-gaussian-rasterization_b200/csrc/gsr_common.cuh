@@ -535,8 +535,6 @@ struct GaussGradOut {
   float* densify_grad_accum;  // optional in/out [P]: += |dL/dmean2D.xy| for visible Gaussians
   float* densify_denom;       // optional in/out [P]: += 1 for visible Gaussians
   float* max_radii2D;         // optional in/out [P]: max(., radius) for visible Gaussians
-  long long mc_delta;         // != 0: NVLS exchange, see gsr_backward_extras
-  float* cam_pos_out;
 };
 
 int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D,

@@ -26,34 +26,6 @@ __device__ __forceinline__ void st3(float* p, int idx, float a, float b, float c
   if (p) { p[3 * idx] = a; p[3 * idx + 1] = b; p[3 * idx + 2] = c; }
 }
 
-// ---- NVLS exchange: gradient stores that go to the multicast alias of a symmetric arena -----------
-// (multimem.* on a multicast address compile to sys-scope REDG / STG; the switch performs the
-// reduction / replication, see gsr_backward_extras in include/gsr_b200.h)
-__device__ __forceinline__ float* mc_alias(float* p, long long mc_delta) {
-  return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + mc_delta);
-}
-__device__ __forceinline__ void mc_red(float* mc, float v) {
-  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
-}
-__device__ __forceinline__ void mc_red4(float* mc, float4 v) {
-  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x),
-               "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ void mc_st(float* mc, float v) {
-  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
-}
-// scene-gradient stores: plain, or in-switch add when the NVLS exchange is on
-__device__ __forceinline__ void sg_st3(float* p, int idx, float a, float b, float c, long long mc) {
-  if (p == nullptr) return;
-  if (mc != 0) {
-    float* q = mc_alias(p + 3 * idx, mc);
-    mc_red(q, a); mc_red(q + 1, b); mc_red(q + 2, c);
-  } else {
-    p[3 * idx] = a; p[3 * idx + 1] = b; p[3 * idx + 2] = c;
-  }
-}
-
 // d(dir/|dir|)/d(dir) applied to dv (auxiliary.h:100-111)
 __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
   const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
@@ -124,18 +96,17 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     if (out.dL_dconic) {
       reinterpret_cast<float4*>(out.dL_dconic)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const bool local = out.mc_delta == 0;  // NVLS: the arena is pre-zeroed, zeros are not sent
-    if (out.dL_dopacity && local) out.dL_dopacity[idx] = 0.f;
+    if (out.dL_dopacity) out.dL_dopacity[idx] = 0.f;
     st3(out.dL_dcolor, idx, 0.f, 0.f, 0.f);
-    if (local) st3(out.dL_dcolor_masked, idx, 0.f, 0.f, 0.f);
+    st3(out.dL_dcolor_masked, idx, 0.f, 0.f, 0.f);
     if (out.dL_ddepth) out.dL_ddepth[idx] = 0.f;
-    if (local) st3(out.dL_dmean3D, idx, 0.f, 0.f, 0.f);
+    st3(out.dL_dmean3D, idx, 0.f, 0.f, 0.f);
     if (out.dL_dcov3D) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) out.dL_dcov3D[(size_t)idx * 6 + k] = 0.f;
     }
-    if (local) st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
-    if (out.dL_drot && local) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
+    if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sh_out) {
       if (TMA) {
         // (no wait needed: nothing is in flight towards this thread's own row)
@@ -286,12 +257,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         const unsigned char cb = clamped[idx];
         const float dR[3] = {g_r * ((cb & 1) ? 0.f : 1.f), g_g * ((cb & 2) ? 0.f : 1.f),
                              g_b * ((cb & 4) ? 0.f : 1.f)};
-        if (out.mc_delta != 0 && out.dL_dcolor_masked != nullptr) {
-          float* q = mc_alias(out.dL_dcolor_masked + 3 * idx, out.mc_delta);
-          mc_st(q, dR[0]); mc_st(q + 1, dR[1]); mc_st(q + 2, dR[2]);
-        } else {
-          st3(out.dL_dcolor_masked, idx, dR[0], dR[1], dR[2]);
-        }
+        st3(out.dL_dcolor_masked, idx, dR[0], dR[1], dR[2]);
         float dx_[3] = {0.f, 0.f, 0.f}, dy_[3] = {0.f, 0.f, 0.f}, dz_[3] = {0.f, 0.f, 0.f};
         float coef[16];
 #pragma unroll
@@ -437,7 +403,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         const float dsx = Rt.c[0][0] * dMt.c[0][0] + Rt.c[0][1] * dMt.c[0][1] + Rt.c[0][2] * dMt.c[0][2];
         const float dsy = Rt.c[1][0] * dMt.c[1][0] + Rt.c[1][1] * dMt.c[1][1] + Rt.c[1][2] * dMt.c[1][2];
         const float dsz = Rt.c[2][0] * dMt.c[2][0] + Rt.c[2][1] * dMt.c[2][1] + Rt.c[2][2] * dMt.c[2][2];
-        sg_st3(out.dL_dscale, idx, dsx, dsy, dsz, out.mc_delta);
+        st3(out.dL_dscale, idx, dsx, dsy, dsz);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           dMt.c[0][j] *= s.x;
@@ -449,16 +415,13 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         dq4.y = 2 * y * (dMt.c[1][0] + dMt.c[0][1]) + 2 * z * (dMt.c[2][0] + dMt.c[0][2]) + 2 * r * (dMt.c[1][2] - dMt.c[2][1]) - 4 * x * (dMt.c[2][2] + dMt.c[1][1]);
         dq4.z = 2 * x * (dMt.c[1][0] + dMt.c[0][1]) + 2 * r * (dMt.c[2][0] - dMt.c[0][2]) + 2 * z * (dMt.c[1][2] + dMt.c[2][1]) - 4 * y * (dMt.c[2][2] + dMt.c[0][0]);
         dq4.w = 2 * r * (dMt.c[0][1] - dMt.c[1][0]) + 2 * x * (dMt.c[2][0] + dMt.c[0][2]) + 2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
-        if (out.dL_drot) {  // w.r.t. the raw quaternion
-          if (out.mc_delta != 0) mc_red4(mc_alias(out.dL_drot + 4 * (size_t)idx, out.mc_delta), dq4);
-          else reinterpret_cast<float4*>(out.dL_drot)[idx] = dq4;
-        }
-      } else if (out.mc_delta == 0) {
+        if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = dq4;  // w.r.t. the raw quaternion
+      } else {
         st3(out.dL_dscale, idx, 0.f, 0.f, 0.f);
         if (out.dL_drot) reinterpret_cast<float4*>(out.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 
-      sg_st3(out.dL_dmean3D, idx, dmean.x, dmean.y, dmean.z, out.mc_delta);
+      st3(out.dL_dmean3D, idx, dmean.x, dmean.y, dmean.z);
       st3(out.dL_dmean2D, idx, g_mx, g_my, 0.f);
       // densification statistics of Inria 3DGS / CG-SLAM mapping (add_densification_stats:
       // xyz_gradient_accum += |viewspace grad.xy|, denom += 1, max_radii2D = max(., radii) over the
@@ -469,10 +432,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       }
       if (out.max_radii2D != nullptr) out.max_radii2D[idx] = fmaxf(out.max_radii2D[idx], (float)radii[idx]);
       if (out.dL_dconic) reinterpret_cast<float4*>(out.dL_dconic)[idx] = make_float4(g_ca, g_cb, 0.f, g_cc);
-      if (out.dL_dopacity) {
-        if (out.mc_delta != 0) mc_red(mc_alias(out.dL_dopacity + idx, out.mc_delta), g_op);
-        else out.dL_dopacity[idx] = g_op;
-      }
+      if (out.dL_dopacity) out.dL_dopacity[idx] = g_op;
       st3(out.dL_dcolor, idx, g_r, g_g, g_b);
       if (out.dL_ddepth) out.dL_ddepth[idx] = g_depth;
     }
@@ -504,11 +464,6 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         pose[11] += dq.x * (-view[2]) + dq.y * (-view[6]) + dq.z * (-view[10]);
       }
     }
-  }
-
-  if (out.mc_delta != 0 && out.cam_pos_out != nullptr && idx == 0) {  // this view's camera position, to every rank
-    float* q = mc_alias(out.cam_pos_out, out.mc_delta);
-    mc_st(q, campos_p[0]); mc_st(q + 1, campos_p[1]); mc_st(q + 2, campos_p[2]);
   }
 
   // dL/dSH out: one bulk store per thread of its own row (TMA) / coalesced store of the block's slab

@@ -12,13 +12,17 @@ reduced.  Two exchange modes:
       so ranks all-gather 3 floats per Gaussian (+ the camera position) and all-reduce only the other
       11 floats; every rank rebuilds the summed dL/dsh locally (`_C.sh_grad_from_views`).  Same result
       up to summation order, 14 instead of 59 floats per Gaussian on the wire.
-  "nvls"  the factorized exchange done INSIDE the backward's per-Gaussian kernel over NVSwitch
-      multicast: the gradient arena is symmetric memory (torch.distributed._symmetric_memory), the kernel
-      adds the 11 reduced floats of every visible Gaussian with multimem.red to the arena's multicast
-      alias (the switch reduces; every rank's replica ends up with the sum) and multicast-stores the
-      masked colour gradient + camera position into its slot of every replica.  No collective call: what
-      is left per step is a memset of the other buffer of the double-buffered arena, one device-side
-      barrier and the local SH rebuild.  Falls back to "factorized_sh" when multicast is unavailable.
+  "nvls"  the factorized exchange with our own kernels over NVSwitch instead of NCCL calls: the flat
+      buffer lives in symmetric memory (torch.distributed._symmetric_memory).  After one device-side
+      barrier every rank (a) all-reduces its 1/world slice of the 11 reduced floats IN THE SWITCH
+      (multimem.ld_reduce pulls and adds the replicas, multimem.st broadcasts the sums:
+      gsr_nvls_allreduce_slice) and (b) rebuilds the summed dL/dsh with a kernel that reads the peers'
+      masked colour gradients in place through P2P loads (gsr_sh_grad_from_view_ptrs) — the all-gather
+      is that kernel's input stream, no gathered copy is written or re-read.  A second barrier ends the
+      step.  Falls back to "factorized_sh" when multicast / symmetric memory is unavailable.
+      (A push variant — multimem.red issued by the backward's per-Gaussian kernel itself — was built
+      and measured first: correct, 4 % faster than NCCL at 2 GPUs, but multimem.red multicasts every
+      operand to every replica, so the ingress grows with the number of ranks: 9 % slower at 8.)
 
 With `attach()` the backward of the B200-native packages writes its gradients straight into the
 flat buffer (no packing copy).  The collectives run on a side stream; `wait()` makes the reduced
@@ -119,59 +123,68 @@ class SceneGradReducer:
         if self._nvls_requested:
             self._setup_nvls(device)
 
-    # ---- NVLS (in-switch) exchange -----------------------------------------------------------------
+    # ---- NVLS exchange (our kernels over NVSwitch: in-switch reduce + P2P-reading SH rebuild) -----------
     def _setup_nvls(self, device):
-        """Allocate the double-buffered symmetric arena; on any failure stay on the NCCL path."""
+        """Move the flat buffer into symmetric memory; on any failure stay on the NCCL path."""
         self.nvls_note = None
         try:
             if not (self.is_cuda and dist.is_available() and dist.is_initialized()) or self._world() < 2:
                 raise RuntimeError("needs CUDA and an initialised process group with world_size > 1")
+            if self.P % 4 != 0:
+                raise RuntimeError("needs a Gaussian count that is a multiple of 4")
             import torch.distributed._symmetric_memory as symm_mem
             world, rank = self._world(), dist.get_rank(self.group)
+            if world > 16:
+                raise RuntimeError("at most 16 ranks")
             group = self.group if self.group is not None else dist.group.WORLD
-            numel = world * self.head + 11 * self.P
-            arenas, handles = [], []
-            for _ in range(2):
-                t = symm_mem.empty(numel, dtype=torch.float32, device=torch.device(device))
-                h = symm_mem.rendezvous(t, group)
-                if not int(h.multicast_ptr):
-                    raise RuntimeError("no multicast support on this system")
-                t.zero_()
-                arenas.append(t)
-                handles.append(h)
+            flat = symm_mem.empty(self.numel, dtype=torch.float32, device=torch.device(device))
+            hdl = symm_mem.rendezvous(flat, group)
+            if not int(hdl.multicast_ptr):
+                raise RuntimeError("no multicast support on this system")
+            flat.zero_()
             torch.cuda.synchronize(device)
-            handles[0].barrier(channel=0, timeout_ms=30000)
+            hdl.barrier(channel=0, timeout_ms=30000)
             torch.cuda.synchronize(device)
-            off = world * self.head
-            red = OrderedDict()
-            for name, n, shape in (("means3D", 3 * self.P, (self.P, 3)), ("opacities", self.P, (self.P, 1)),
-                                   ("scales", 3 * self.P, (self.P, 3)), ("rotations", 4 * self.P, (self.P, 4))):
-                red[name] = (off, n, shape)
-                off += n
-            self.nvls = dict(arenas=arenas, handles=handles, cur=0, done=None, world=world, rank=rank, slices=red)
+            self.flat = flat          # same layout as "factorized_sh": [dR 3P | campos 3 | pad | reduced 11P]
+            self.nvls = dict(handle=hdl, world=world, rank=rank, mc=int(hdl.multicast_ptr),
+                             peers=[int(p) for p in hdl.buffer_ptrs])
+            import os
+            if os.environ.get("GSR_DP_TIMING"):   # per-phase CUDA events, see nvls_timing()
+                self.nvls["timing"] = []
             self.mode = "nvls"
         except Exception as e:  # noqa: BLE001 - any failure means: use the NCCL exchange
             self.nvls = None
             self.nvls_note = "nvls unavailable (%s: %s); using factorized_sh" % (type(e).__name__, e)
 
-    def _nvls_register(self):
-        n = self.nvls
-        self._attached._C.set_grad_arena_nvls(n["arenas"][n["cur"]], int(n["handles"][n["cur"]].multicast_ptr),
-                                              n["rank"], n["world"])
+    def nvls_timing(self):
+        """Mean milliseconds of (barrier A, slice all-reduce, SH rebuild, barrier B) over the recorded
+        steps (GSR_DP_TIMING=1), skipping the first five."""
+        t = (self.nvls or {}).get("timing") or []
+        torch.cuda.synchronize()
+        rows = [[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in t[5:]]
+        return [sum(r[i] for r in rows) / max(1, len(rows)) for i in range(4)] if rows else None
 
     def _nvls_exchange(self):
-        """Runs on the side stream after the backward: zero the other buffer, barrier, rebuild dL/dsh."""
-        n = self.nvls
-        cur, nxt = n["cur"], 1 - n["cur"]
-        n["arenas"][nxt].zero_()
-        n["handles"][cur].barrier(channel=0, timeout_ms=30000)
-        gathered = n["arenas"][cur][:n["world"] * self.head].view(n["world"], self.head)
-        self.sh_sum = self._attached._C.sh_grad_from_views(self.means3D.detach(), gathered, self.sh_degree, self.M)
+        """Side stream, after the backward wrote this rank's gradients into its replica."""
+        n, C = self.nvls, self._attached._C
+        timing = n.get("timing")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timing is not None else None
+        mark = (lambda i: ev[i].record()) if ev else (lambda i: None)
+        mark(0)
+        n["handle"].barrier(channel=0, timeout_ms=30000)        # every rank's gradients are in place
+        mark(1)
+        C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"])
+        mark(2)
+        self.sh_sum = C.sh_grad_from_view_ptrs(self.means3D.detach(), n["peers"],
+                                               [p + 4 * 3 * self.P for p in n["peers"]], self.sh_degree, self.M)
+        mark(3)
+        n["handle"].barrier(channel=1, timeout_ms=30000)        # all slices broadcast, all peer reads done
+        mark(4)
+        if ev:
+            timing.append(ev)
         if self.average:
-            n["arenas"][cur][n["world"] * self.head:].div_(n["world"])
+            self.flat[self.head:].div_(n["world"])
             self.sh_sum.div_(n["world"])
-        n["done"] = cur
-        n["cur"] = nxt
 
     # ---- wiring -------------------------------------------------------------------------------
     def attach(self, rasterizer_module):
@@ -184,10 +197,7 @@ class SceneGradReducer:
                 self.mode, self.nvls = "factorized_sh", None
             return False
         self._attached = rasterizer_module
-        if self.mode == "nvls":
-            self._nvls_register()
-        else:
-            fn(self.flat, self.mode == "factorized_sh")
+        fn(self.flat, self.mode in ("factorized_sh", "nvls"))
         return True
 
     def detach(self):
@@ -197,14 +207,8 @@ class SceneGradReducer:
 
     def views(self):
         """Per-parameter reduced gradients (valid after wait())."""
-        if self.mode == "nvls":
-            n = self.nvls
-            buf = n["arenas"][n["done"] if n["done"] is not None else n["cur"]]
-            out = {k: buf[o:o + m].view(shape) for k, (o, m, shape) in n["slices"].items()}
-            out["shs"] = self.sh_sum
-            return out
         out = {k: self.flat[o:o + n].view(shape) for k, (o, n, shape) in self.slices.items()}
-        if self.mode == "factorized_sh":
+        if self.mode in ("factorized_sh", "nvls"):
             out["shs"] = self.sh_sum
         return out
 
@@ -212,16 +216,11 @@ class SceneGradReducer:
         for k, (o, n, _shape) in self.slices.items():
             g = grads.get(k)
             self.flat[o:o + n].copy_(g.reshape(-1) if g is not None else 0)
-        if self.mode == "factorized_sh":
+        if self.mode in ("factorized_sh", "nvls"):
             self.flat[:3 * self.P].copy_(masked_color.reshape(-1))
             self.flat[3 * self.P:3 * self.P + 3].copy_(campos.reshape(-1)[:3])
 
     def _aliases_flat(self, grads):
-        if self.mode == "nvls":
-            n = self.nvls
-            lo = n["arenas"][n["cur"]].data_ptr()
-            return all(grads.get(k) is not None and grads[k].data_ptr() == lo + 4 * o
-                       for k, (o, _m, _s) in n["slices"].items())
         lo = self.flat.data_ptr()
         for k, (o, _n, _shape) in self.slices.items():
             g = grads.get(k)
@@ -265,23 +264,17 @@ class SceneGradReducer:
     def reduce_async(self, grads=None, masked_color=None, campos=None):
         """Pack (unless the gradients already live in the flat buffer, see attach()) and launch the
         exchange.  Returns immediately on CUDA; call wait() before reading views()."""
-        if self.mode == "nvls":
-            if grads is not None and not self._aliases_flat(grads):
-                raise RuntimeError("nvls exchange: the gradients were not produced into the symmetric arena "
-                                   "(attach() the rasterizer package and call wait() after every reduce_async())")
-            self.stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.stream):
-                self._nvls_exchange()
-                self._done = torch.cuda.Event()
-                self._done.record(self.stream)
-            self._nvls_register()   # the next backward writes into the other buffer
-            return
+        if self.mode == "nvls" and self._attached is None:
+            raise RuntimeError("nvls exchange needs attach() to a B200-native rasterizer package")
         if grads is not None and not (self._attached is not None and self._aliases_flat(grads)):
             self.pack(grads, masked_color, campos)
         if self.is_cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                self._exchange()
+                if self.mode == "nvls":
+                    self._nvls_exchange()
+                else:
+                    self._exchange()
                 self._done = torch.cuda.Event()
                 self._done.record(self.stream)
         else:
@@ -295,6 +288,4 @@ class SceneGradReducer:
 
     def bytes_per_step(self):
         """fp32 bytes this rank contributes to the exchange per step."""
-        if self.mode == "nvls":
-            return (14 * self.P + 4) * 4
         return self.numel * 4

@@ -131,16 +131,6 @@ typedef struct gsr_backward_extras {
   float* densify_grad_accum;
   float* densify_denom;
   float* max_radii2D;
-  /* In-switch gradient exchange for view-level data parallelism over NVSwitch multicast (NVLS).
-   * mc_delta != 0 says: dL_dmean3D, dL_dopacity, dL_dscale, dL_drot and dL_dcolor_masked point into
-   * THIS rank's replica of a symmetric arena whose multicast alias lies mc_delta bytes further.  The
-   * per-Gaussian backward kernel then does not store those gradients locally but issues, for visible
-   * Gaussians only, multimem.red.add (the four reduced gradients: every rank's replica of a pre-zeroed
-   * arena ends up holding the SUM over ranks) and multimem.st (the masked colour gradient and, if
-   * cam_pos_out != NULL, the camera position — written into this rank's slot of every replica).
-   * The exchange is thereby part of the kernel that produces the gradients: no separate collective. */
-  long long mc_delta;
-  float* cam_pos_out;      /* [3] inside the arena (local address); NULL = not wanted */
 } gsr_backward_extras;
 
 /* ---- light variant ---------------------------------------------------------------------- */
@@ -236,6 +226,21 @@ GSR_API int gsr_sh_grad_from_views(int P, int D, int M, const float* means3D, in
                                    const float* dR_all, size_t view_stride,
                                    const float* campos_all, size_t campos_stride,
                                    float* dL_dsh, void* stream);
+
+/* The same sum with the views' gradients read IN PLACE (at most 16 views): dR_ptrs[v] -> [P,3] masked colour
+ * gradient of view v, campos_ptrs[v] -> its camera position [3]; the pointers (HOST arrays of DEVICE
+ * pointers) may point into peer GPUs' memory (symmetric memory / P2P mappings): the all-gather of
+ * view-level data parallelism then happens as the P2P loads of this kernel. */
+GSR_API int gsr_sh_grad_from_view_ptrs(int P, int D, int M, const float* means3D, int nviews,
+                                       const float* const* dR_ptrs, const float* const* campos_ptrs,
+                                       float* dL_dsh, void* stream);
+
+/* In-switch (NVLS) all-reduce of this rank's 1/world slice of count_floats floats starting
+ * offset_floats into a symmetric buffer, given the buffer's MULTICAST alias: multimem.ld_reduce sums
+ * the replicas in the NVSwitch, multimem.st writes the sums back to every replica.  All ranks call it
+ * (between two barriers of their own) and the whole range is all-reduced.  offset / count: multiples of 4. */
+GSR_API int gsr_nvls_allreduce_slice(float* multicast_ptr, size_t offset_floats, size_t count_floats,
+                                     int rank, int world, void* stream);
 
 /* ---- pose tracker (not part of the reference surface) ------------
  * K iterations of CG-SLAM's tracking loop — render(-light, map_off) -> masked L1 colour + depth loss
