@@ -55,6 +55,28 @@ def test_invalid_arguments_are_rejected_without_a_gpu(built):
     assert lib.gsr_decode_geometry(None, 3, None, None, None, None, None, None, None, None) == -1
 
 
+def test_extension_entry_points_validate_arguments_without_a_gpu(built):
+    """Tracker, P2P SH rebuild and NVLS slice all-reduce reject bad arguments before any CUDA call."""
+    lib = ctypes.CDLL(built.core_library_path())
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    lib.gsr_tracker_create.restype = ctypes.c_void_p
+    assert lib.gsr_tracker_create(0, 3, 16, 64, 48, ctypes.c_float(1.0), ctypes.c_float(1.0), None, 8) is None
+    assert b"bad arguments" in lib.gsr_last_error()
+    assert lib.gsr_tracker_run(None, None, 1, None, None) == -1
+    assert lib.gsr_tracker_set_scene(None, None, None, None, None, None, ctypes.c_float(1.0), None, None, None) == -1
+    assert lib.gsr_tracker_set_frame(None, None, None) == -1
+    assert lib.gsr_tracker_set_pose(None, None, None) == -1
+    lib.gsr_tracker_destroy(None)  # no-op
+    # offset not a multiple of 4 floats / NULL multicast pointer / rank out of range
+    f = ctypes.c_void_p(256)
+    assert lib.gsr_nvls_allreduce_slice(None, ctypes.c_size_t(0), ctypes.c_size_t(16), 0, 2, None) == -1
+    assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(2), ctypes.c_size_t(16), 0, 2, None) == -1
+    assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(0), ctypes.c_size_t(16), 2, 2, None) == -1
+    assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, None, 1, None, None, None, None) == -1
+    assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, f, 17, f, f, f, None) == -1   # more than 16 views
+    assert lib.gsr_sh_grad_from_view_ptrs(0, 3, 16, None, 0, None, None, None, None) == 0
+
+
 @pytest.mark.parametrize("variant", ["light", "full"])
 def test_shim_exports_reference_surface(built, variant):
     mod = built.load_variant(variant)

@@ -65,7 +65,7 @@ def test_flat_gradient_allreduce_world2():
     assert res[0][2] == [0, 2, 4] and res[1][2] == [1, 3]
 
 
-def _worker_fact(rank, world, port, P, M, q):
+def _worker_fact(rank, world, port, P, M, q, mode="factorized_sh"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -83,8 +83,10 @@ def _worker_fact(rank, world, port, P, M, q):
         return grads, dR, campos
 
     grads, dR, campos = rank_data(rank)
-    red = dp.SceneGradReducer(shapes, "cpu", mode="factorized_sh", means3D=means, sh_degree=3)
+    red = dp.SceneGradReducer(shapes, "cpu", mode=mode, means3D=means, sh_degree=3)
     assert red.numel == 14 * P + 4
+    if mode == "nvls":  # no CUDA / no NVSwitch here: the reducer must say so and use the NCCL-style exchange
+        assert red.mode == "factorized_sh" and red.nvls is None and "nvls unavailable" in red.nvls_note
     red.reduce_async(grads, masked_color=dR, campos=campos)
     views = red.wait()
     ok = True
@@ -108,6 +110,21 @@ def test_factorized_sh_exchange_world2():
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker_fact, args=(r, world, port, P, M, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_nvls_mode_falls_back_to_factorized_exchange_without_multicast():
+    world, P, M = 2, 64, 16
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fact, args=(r, world, port, P, M, q, "nvls")) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
