@@ -623,6 +623,11 @@ def test_factorized_sh_exchange_matches_summed_sh_gradients(built, variant):
         out = mod._C.sh_grad_from_views(means_dev, gathered, 3, 16).cpu().numpy()
         rel, bad = pu.grad_mismatch(out, sh_sum, rtol=1e-3)
         assert rel < 1e-4 and bad < 1e-3, (rel, bad)
+        # the pointer-table variant (what the NVLS exchange feeds with peer pointers) reads the same
+        # rows in place and must give the same sums, also for a ragged last block (P not a multiple of 128)
+        ptrs = [int(gathered[v].data_ptr()) for v in range(gathered.shape[0])]
+        out2 = mod._C.sh_grad_from_view_ptrs(means_dev, ptrs, [p + 4 * 3 * 2000 for p in ptrs], 3, 16).cpu().numpy()
+        assert np.allclose(out2, out, rtol=1e-6, atol=1e-9)
         # single-process exchange path end to end
         red.reduce_async()
         v = red.wait()
