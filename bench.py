@@ -462,7 +462,8 @@ def main():
     if reducer is not None and getattr(reducer, "nvls", None) and rank == 0:
         tt = reducer.nvls_timing()
         if tt:
-            log("nvls exchange phases (ms): barrier A %.3f, slice all-reduce %.3f, SH rebuild (P2P) %.3f, barrier B %.3f" % tuple(tt))
+            log("nvls exchange phases (ms): barrier A %.3f, (slice all-reduce launched on a second stream %.3f), "
+                "SH rebuild (P2P) overlapped with the slice all-reduce %.3f, barrier B %.3f" % tuple(tt))
     if world > 1:
         dist.barrier()
     if rank != 0:

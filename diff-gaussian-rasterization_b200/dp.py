@@ -157,8 +157,9 @@ class SceneGradReducer:
             self.nvls_note = "nvls unavailable (%s: %s); using factorized_sh" % (type(e).__name__, e)
 
     def nvls_timing(self):
-        """Mean milliseconds of (barrier A, slice all-reduce, SH rebuild, barrier B) over the recorded
-        steps (GSR_DP_TIMING=1), skipping the first five."""
+        """Mean milliseconds of (barrier A, launch of the slice all-reduce on its own stream, SH rebuild
+        overlapped with that all-reduce, barrier B) over the recorded steps (GSR_DP_TIMING=1), skipping
+        the first five."""
         t = (self.nvls or {}).get("timing") or []
         torch.cuda.synchronize()
         rows = [[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in t[5:]]
@@ -173,10 +174,19 @@ class SceneGradReducer:
         mark(0)
         n["handle"].barrier(channel=0, timeout_ms=30000)        # every rank's gradients are in place
         mark(1)
-        C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"])
+        # the slice all-reduce (bound by switch round trips) and the P2P SH rebuild (bound by peer reads)
+        # are independent: they run side by side on two streams
+        side = n.get("stream2")
+        if side is None:
+            side = n["stream2"] = torch.cuda.Stream(device=self.flat.device)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"])
         mark(2)
         self.sh_sum = C.sh_grad_from_view_ptrs(self.means3D.detach(), n["peers"],
                                                [p + 4 * 3 * self.P for p in n["peers"]], self.sh_degree, self.M)
+        cur.wait_stream(side)
         mark(3)
         n["handle"].barrier(channel=1, timeout_ms=30000)        # all slices broadcast, all peer reads done
         mark(4)
