@@ -197,17 +197,33 @@ class Frame:
 
     def _upload(self):
         """Enqueue the H2D copies of ONE step's per-frame inputs (camera, gt depth, cotangents) from
-        pinned host memory on the copy stream; returns the device tensors and a completion event."""
+        pinned host memory on the copy stream, into one of two preallocated device input sets (no
+        allocator traffic inside the timed region: per-step allocations on a side stream made the
+        caching allocator fall back to cudaMalloc now and then, which showed as 5x outliers).
+        Returns the device tensors, a completion event and the slot index."""
         torch, dev = self.torch, self.device
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=dev)
+            mk = lambda h: torch.empty_like(h, device=dev)
+            self.dev_in = [dict(view=mk(self.h_view), proj=mk(self.h_proj), campos=mk(self.h_campos),
+                                gt=mk(self.h_gt), cots=[mk(c) for c in self.h_cots]) for _ in range(2)]
+            self.slot_free = [None, None]
+            self.uploads = 0
+        slot = self.uploads & 1
+        self.uploads += 1
+        d = self.dev_in[slot]
         with torch.cuda.stream(self.copy_stream):
-            d = dict(view=self.h_view.to(dev, non_blocking=True), proj=self.h_proj.to(dev, non_blocking=True),
-                     campos=self.h_campos.to(dev, non_blocking=True), gt=self.h_gt.to(dev, non_blocking=True),
-                     cots=[c.to(dev, non_blocking=True) for c in self.h_cots])
+            if self.slot_free[slot] is not None:      # the step that consumed this set has finished
+                self.copy_stream.wait_event(self.slot_free[slot])
+            d["view"].copy_(self.h_view, non_blocking=True)
+            d["proj"].copy_(self.h_proj, non_blocking=True)
+            d["campos"].copy_(self.h_campos, non_blocking=True)
+            d["gt"].copy_(self.h_gt, non_blocking=True)
+            for dc, hc in zip(d["cots"], self.h_cots):
+                dc.copy_(hc, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return d, ev
+        return d, ev, slot
 
     def step_e2e(self):
         """Same frame with the per-frame inputs coming from pinned host memory and the result
@@ -219,12 +235,10 @@ class Frame:
         main = torch.cuda.current_stream()
         if self.pending is None:
             self.pending = self._upload()
-        inp, ev = self.pending
+        inp, ev, in_slot = self.pending
         self.pending = self._upload()
         main.wait_event(ev)
-        for t in [inp["view"], inp["proj"], inp["campos"], inp["gt"]] + inp["cots"]:
-            t.record_stream(main)
-        view = inp["view"].requires_grad_(True)
+        view = inp["view"].detach().requires_grad_(True)   # fresh leaf on the reused storage
         rast = self._rasterizer(view.detach(), inp["proj"], inp["campos"])
         p = self.params
         res = rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"], shs=p["shs"],
@@ -243,6 +257,7 @@ class Frame:
         self.h_results[slot].copy_(packed, non_blocking=True)
         self.res_ev[slot] = torch.cuda.Event()
         self.res_ev[slot].record(main)
+        self.slot_free[in_slot] = self.res_ev[slot]   # this step's device inputs may be overwritten after it
         return value
 
 
