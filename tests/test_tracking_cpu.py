@@ -127,6 +127,28 @@ def test_masked_l1_matches_autograd():
     np.testing.assert_allclose(dd, depth.grad.numpy())
 
 
+@pytest.mark.parametrize("axis,deg", [((1, 0, 0), 10), ((0, 1, 0), 179), ((0, 0, 1), 179), ((1, 0, 0), 179),
+                                      ((1, 2, 3), 120), ((-1, 1, 0.5), 65)])
+def test_rotation_quaternion_round_trip(axis, deg):
+    """rotation_to_quat covers all four branches (trace > 0 and the three dominant diagonals)."""
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    th = np.radians(deg)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+    q = trk.rotation_to_quat(torch.tensor(R))
+    assert abs(float(q.norm()) - 1.0) < 1e-6
+    np.testing.assert_allclose(trk.quat_to_rotation(q.double()).numpy(), R, atol=1e-6)
+    np.testing.assert_allclose(po.quat_to_R(q.numpy()), R, atol=1e-6)
+
+
+def test_default_params_and_struct_layout():
+    prm = trk.default_params(w_color=0.25, lr_rot=1e-3)
+    assert prm["w_color"] == 0.25 and prm["lr_rot"] == 1e-3 and prm["beta2"] == 0.999 and prm["use_depth_mask"] is True
+    cp = trk.TrackParams(1.0, 2.0, 0.5, 1, 1e-3, 2e-3, 0.9, 0.999, 1e-8)
+    assert abs(cp.w_depth - 2.0) < 1e-7 and cp.use_depth_mask == 1 and abs(cp.eps - 1e-8) < 1e-12
+
+
 def test_tracker_symbols_exported():
     lib = ctypes.CDLL(ge.core_library_path())
     for name in ("gsr_tracker_create", "gsr_tracker_destroy", "gsr_tracker_set_scene",
