@@ -1,0 +1,64 @@
+"""CPU check of the built CUDA objects: the sm_100a SASS contains the instructions DESIGN.md claims
+(B200_PROFILING.md: `UBLKCP` / `SYNCS.*` prove cp.async.bulk + mbarrier, `FFMA2` the packed fp32x2
+arithmetic, `REDG` the warp-reduced gradient atomics, sys-scope `LDG/REDG/STG ... .SYS` the multimem
+(NVLS) operations) and nothing was compiled for another architecture.  Skipped when cuobjdump is absent."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "diff-gaussian-rasterization_b200", "build")
+LIB = os.path.join(ROOT, "diff-gaussian-rasterization_b200", "lib", "libgsr_b200.so")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not available")
+
+
+def _sass(obj):
+    return subprocess.run([CUOBJDUMP, "-sass", os.path.join(OBJ, obj)], capture_output=True, text=True).stdout
+
+
+def _count(text, pattern):
+    return len(re.findall(pattern, text))
+
+
+def test_library_is_sm_100a_only(built):
+    out = subprocess.run([CUOBJDUMP, "-lelf", LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_per_gaussian_kernels_use_bulk_async_copies(built):
+    fwd, bwd = _sass("preprocess_fwd.o"), _sass("preprocess_bwd.o")
+    assert _count(fwd, r"UBLKCP\.S\.G") >= 1                      # global -> shared SH rows
+    assert _count(bwd, r"UBLKCP\.S\.G") >= 1 and _count(bwd, r"UBLKCP\.G\.S") >= 1   # and dL/dSH rows back
+    for text in (fwd, bwd):
+        assert _count(text, r"SYNCS\.ARRIVE\.TRANS64") >= 1      # mbarrier arrive / expect_tx
+        assert _count(text, r"SYNCS\.PHASECHK\.TRANS64\.TRYWAIT") >= 1
+
+
+def test_backward_blend_uses_packed_fp32x2_and_warp_reduced_atomics(built):
+    bwd = _sass("render_bwd.o")
+    assert _count(bwd, r"\bFFMA2\b") >= 20 and _count(bwd, r"\bFMUL2\b") >= 20 and _count(bwd, r"\bFADD2\b") >= 5
+    assert _count(bwd, r"REDG\.E\.ADD\.F32") >= 1                 # one coalesced red per (warp, Gaussian, slot)
+    assert _count(bwd, r"\bATOMG\b") == 0                         # no returning atomics in the blend
+
+
+def test_forward_blend_has_no_spills_and_keeps_its_occupancy(built):
+    out = subprocess.run([CUOBJDUMP, "-res-usage", os.path.join(OBJ, "render_fwd.o")], capture_output=True,
+                         text=True).stdout
+    stacks = [int(v) for v in re.findall(r"STACK:(\d+)", out)]
+    regs = [int(v) for v in re.findall(r"REG:(\d+)", out)]
+    assert stacks and all(v == 0 for v in stacks), stacks        # no spills
+    assert sorted(regs)[:2] == [48, 48] or max(sorted(regs)[:2]) <= 51, regs   # image variants: 5 CTAs of 256 threads per SM
+    assert max(regs) <= 64, regs                                  # fused-loss (tracker) variant: 4 CTAs per SM
+
+
+def test_nvls_kernels_use_sys_scope_multimem_operations(built):
+    sh = _sass("sh_grad_views.o")
+    # multimem.ld_reduce -> LDGMC (load with in-switch reduction), multimem.st -> sys-scope STG.128
+    assert _count(sh, r"LDGMC\.E\.ADD\.F32x4") >= 1, "no multimem.ld_reduce in sh_grad_views.o"
+    assert _count(sh, r"STG\.E\.128\.STRONG\.SYS") >= 1
