@@ -432,8 +432,15 @@ def main():
             r = mod._C.rasterize_gaussians(*args, False)
             num_rendered = int(r[0])
         else:
-            r = mod._C.rasterize_gaussians(*args)
-            num_rendered, num_related = int(r[0]), int(r[1])
+            # NG (valid (pixel, Gaussian) pairs) is only counted on request: one probe with "exact_ng"
+            lib_probe = ctypes.CDLL(ge.core_library_path()) if a.impl == "b200" else None
+            old_ng = lib_probe.gsr_set_option(b"exact_ng", 1) if lib_probe is not None else None
+            try:
+                r = mod._C.rasterize_gaussians(*args)
+                num_rendered, num_related = int(r[0]), int(r[1])
+            finally:
+                if lib_probe is not None and old_ng is not None and old_ng >= 0:
+                    lib_probe.gsr_set_option(b"exact_ng", old_ng)
         del r
         if os.environ.get("GSR_BENCH_DEBUG"):
             import hashlib
@@ -497,6 +504,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "variant": a.variant, "gaussians": P, "width": W, "height": H,
                    "num_rendered": num_rendered, "num_related": num_related,
+                   "mean_tile_list": (num_rendered / float(((W + 15) // 16) * ((H + 15) // 16))) if num_rendered else None,
+                   "mean_valid_contributors_per_pixel": (num_related / float(W * H)) if num_related else None,
                    "parallelism": ("view-dp%d (one view per GPU; exchange '%s': %d MB of scene gradients per rank "
                                    "and step)" % (world, reducer.mode, reducer.bytes_per_step() >> 20))
                    if world > 1 else "single GPU",
