@@ -205,3 +205,59 @@ def test_light_colour_gradients_match_finite_differences():
             fd = (loss(fwd(cp, scene.opacities)) - loss(fwd(cm, scene.opacities))) / (2 * eps)
             assert abs(fd - g["colors"][i, ch]) <= 1e-4 * max(1.0, abs(fd))
     r0.close()
+
+
+# ---- 3. size-independent properties (the same ones the GPU suite checks on the CUDA path at full
+#         size, here on the oracle at a size it finishes in a second) --------------------------------
+
+def _small(seed=11, P=400, W=96, H=64):
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(W, H)
+    return sc, cam, sc.make_scene(P, cam, (2.0, 10.0), seed=seed)
+
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_backward_is_linear_in_the_cotangents(variant):
+    sc, cam, scene = _small()
+    n_aux = 3 if variant == "light" else 2
+    c1 = sc.make_cotangents(cam, n_aux, seed=1)
+    c2 = sc.make_cotangents(cam, n_aux, seed=2)
+    if variant == "light":      # depth_var's backward term is quadratic in nothing but carries gt: keep it linear
+        c1[1][2].zero_()
+        c2[1][2].zero_()
+    mix = (c1[0] + 2.0 * c2[0], [a + 2.0 * b for a, b in zip(c1[1], c2[1])])
+    _, g1 = pu.run_oracle(variant, cam, scene, c1, precision="f64")
+    _, g2 = pu.run_oracle(variant, cam, scene, c2, precision="f64")
+    _, gm = pu.run_oracle(variant, cam, scene, mix, precision="f64")
+    for k in g1:
+        if g1[k] is None:
+            continue
+        want = g1[k].astype(np.float64) + 2.0 * g2[k].astype(np.float64)
+        scale = max(1e-30, float(np.abs(want).max()))
+        assert float(np.abs(gm[k] - want).max()) <= 1e-6 * scale, k   # results come back as float32
+
+
+def test_background_enters_only_through_the_final_transmittance():
+    sc, cam, scene = _small(seed=12)
+    cot = sc.make_cotangents(cam, 3)
+    o1, _ = pu.run_oracle("light", cam, scene, cot, backward=False, precision="f64")
+    scene2 = scene._replace(bg=torch.tensor([0.9, 0.1, 0.5]))
+    o2, _ = pu.run_oracle("light", cam, scene2, cot, backward=False, precision="f64")
+    T = 1.0 - o1["opacity_map"].astype(np.float64)          # light: alpha map = sum alpha*T = 1 - T_final
+    dbg = (scene2.bg - scene.bg).numpy().astype(np.float64)
+    np.testing.assert_allclose(o2["color"] - o1["color"], dbg[:, None, None] * T, atol=1e-6)
+    for k in ("depth", "depth_median", "opacity_map", "radii"):
+        np.testing.assert_array_equal(o1[k], o2[k])
+
+
+def test_gaussians_behind_the_camera_get_no_radius_and_no_gradient():
+    sc, cam, scene = _small(seed=13, P=300)
+    cot = sc.make_cotangents(cam, 2)
+    outs, grads = pu.run_oracle("full", cam, scene, cot)
+    w2c = cam.w2c.numpy().astype(np.float64)
+    z = scene.means3D.numpy().astype(np.float64) @ w2c[2, :3] + w2c[2, 3]
+    behind = z <= 0.2
+    assert behind.any() and (~behind).any()
+    assert (outs["radii"][behind] == 0).all()
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "means2D"):
+        assert float(np.abs(grads[k][behind]).max()) == 0.0, k
