@@ -15,7 +15,7 @@ namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_prefetch=*/0};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -214,6 +214,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "track_headroom_pct")) return &g_opts.track_headroom_pct;
   if (!strcmp(key, "bulk_sh")) return &g_opts.bulk_sh;
   if (!strcmp(key, "cnt_stride")) return &g_opts.cnt_stride;
+  if (!strcmp(key, "bwd_prefetch")) return &g_opts.bwd_prefetch;
   return nullptr;
 }
 

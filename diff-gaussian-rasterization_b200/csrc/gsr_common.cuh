@@ -52,6 +52,7 @@ struct Options {
   int track_headroom_pct;
   int bulk_sh;
   int cnt_stride;
+  int bwd_prefetch;
 };
 Options& options();
 inline int cnt_stride() { const int s = options().cnt_stride; return (s >= 1 && s <= kCntStrideMax) ? s : 1; }

@@ -95,6 +95,9 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *   "cnt_stride"    spacing (in 32-bit words, 1..32, default 8 = one per 32-byte sector) of the per-tile
  *                   entry counters / scatter cursors: neighbouring tiles' atomics no longer serialise on
  *                   one cache line (measured: preprocess_fwd 0.078 -> 0.069 ms, scatter 0.059 -> 0.042 ms).
+ *   "bwd_prefetch"  0 (default): the packed backward blend kernel gathers a round's records in front of the
+ *                   round; 1: it prefetches the next round's records with cp.async underneath the current
+ *                   round (same results; written from the ncu stall profile, not yet timed on a GPU).
  *   "track_headroom_pct" head room (percent, default 50) of the tracker's binning buffer over the
  *                   counts of its probing forward; negative values force the overflow / retry path
  *                   (test hook).
