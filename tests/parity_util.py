@@ -139,25 +139,36 @@ def grad_mismatch(a, b, rtol=GRAD_RTOL):
 
 
 def compare_runs(outs_a, grads_a, outs_b, grads_b, flip_budget=2e-4, grad_budget=2e-3,
-                 label_a="ours", label_b="ref"):
-    """Compare two (outputs, grads) pairs; returns (ok, report lines)."""
+                 label_a="ours", label_b="ref", strict=False, stats=None):
+    """Compare two (outputs, grads) pairs; returns (ok, report lines).
+
+    strict=True is the north star's gate, used against the reference build (golden vectors and live
+    runs): ZERO image elements outside 1e-4, integer outputs exactly equal, every gradient within
+    1e-3 of the tensor's largest magnitude.  strict=False (CUDA vs the CPU oracle, whose expf / FMA
+    contraction differ in the last bit) keeps small budgets for flipped hard decisions (alpha < 15/255,
+    T < 1e-4, median crossing); the gradient bar is the same 1e-3.
+    `stats`, when given, receives the violation counts (bench.py's "parity" object)."""
     ok = True
     lines = []
+    st = dict(fwd_max_abs=0.0, pixels_over=0, int_mismatches=0, grad_max_rel=0.0, grad_frac_bad_max=0.0)
     for k in outs_a:
         a, b = outs_a[k], outs_b.get(k)
         if b is None:
             continue
         if k in ("radii", "gau_related_pixels"):
             nbad = int((np.asarray(a) != np.asarray(b)).sum())
-            good = nbad <= max(1, int(flip_budget * a.size))
+            good = nbad == 0 if strict else nbad <= max(1, int(flip_budget * a.size))
+            st["int_mismatches"] += nbad
             lines.append("%-20s int mismatches %d / %d %s" % (k, nbad, a.size, "" if good else "FAIL"))
         elif k == "gau_uncertainty":
             g, fb = grad_mismatch(a, b)
-            good = fb <= grad_budget
+            good = g <= GRAD_RTOL and fb <= grad_budget
             lines.append("%-20s rel %.3e frac_bad %.3e %s" % (k, g, fb, "" if good else "FAIL"))
         else:
             nbad, mx, n = image_mismatch(a, b)
-            good = nbad <= max(2, int(flip_budget * n))
+            good = nbad == 0 if strict else nbad <= max(2, int(flip_budget * n))
+            st["pixels_over"] += nbad
+            st["fwd_max_abs"] = max(st["fwd_max_abs"], mx)
             lines.append("%-20s >%.0e: %d / %d  max %.3e %s" % (k, FWD_ATOL, nbad, n, mx, "" if good else "FAIL"))
         ok &= good
     for k in grads_a:
@@ -165,9 +176,13 @@ def compare_runs(outs_a, grads_a, outs_b, grads_b, flip_budget=2e-4, grad_budget
         if a is None or b is None:
             continue
         g, fb = grad_mismatch(a, b)
-        good = (g <= 5 * GRAD_RTOL and fb <= grad_budget) if k != "viewmatrix" else g <= GRAD_RTOL
+        good = g <= GRAD_RTOL and (fb <= grad_budget or k == "viewmatrix")
+        st["grad_max_rel"] = max(st["grad_max_rel"], g)
+        st["grad_frac_bad_max"] = max(st["grad_frac_bad_max"], fb)
         lines.append("grad %-15s global_rel %.3e frac_bad %.3e %s" % (k, g, fb, "" if good else "FAIL"))
         ok &= good
+    if stats is not None:
+        stats.update(st)
     return ok, lines
 
 

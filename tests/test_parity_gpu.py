@@ -95,8 +95,8 @@ def test_cuda_matches_reference_golden(built, name):
                                      use_sh=g["use_sh"], sh_degree=g["sh_degree"], track_off=track_off,
                                      map_off=map_off, cov_precomp=g["cov"])
         assert (outs["radii"] == exp_o["radii"]).all()
-        ok, lines = pu.compare_runs(outs, grads, exp_o, exp_g, flip_budget=0.0, grad_budget=1e-3,
-                                    label_b="reference")
+        ok, lines = pu.compare_runs(outs, grads, exp_o, exp_g, grad_budget=1e-3, label_b="reference",
+                                    strict=True)
         assert ok, "%s track_off=%s map_off=%s\n%s" % (name, track_off, map_off, "\n".join(lines))
         # forward images are bit-identical to the reference build (pinned arithmetic)
         for k in ("color", "depth"):
@@ -173,9 +173,53 @@ def test_cuda_matches_reference_build_live(built, variant):
     mod = built.load_variant(variant)
     o_m, g_m = pu.run_variant(mod, variant, cam, scene, cot)
     o_r, g_r = pu.run_variant(ref, variant, cam, scene, cot)
-    ok, lines = pu.compare_runs(o_m, g_m, o_r, g_r, flip_budget=0.0, grad_budget=1e-3)
+    ok, lines = pu.compare_runs(o_m, g_m, o_r, g_r, grad_budget=1e-3, strict=True)
     assert ok, "\n".join(lines)
     assert np.array_equal(o_m["color"], o_r["color"])
+
+
+# The configurations bench.py times (BASELINE.json configs C2-C4), against the reference build on the
+# same tensors, at the north star's tolerances with NO budgets: 0 image elements over 1e-4, integer
+# outputs equal, every gradient within 1e-3 of its tensor's largest magnitude.  -full's dL/dviewmatrix
+# is compared on the 16-aligned, fully covered variant of C3 only (1920x1088 with a backdrop): at
+# 1920x1080 the reference's ComputePG reads uninitialised shared memory in the partly-outside bottom
+# tile row, so its own value is not reproducible there.
+TIMED = [
+    ("C2", "light", False, False), ("C2", "light", True, False), ("C2", "light", False, True),
+    ("C3", "light", False, False), ("C3", "full", False, False), ("C3a", "full", False, False),
+    ("C4", "light", False, False), ("C4", "full", False, False),
+]
+
+
+def _timed_case(name):
+    sc = ge.load_scene_module()
+    if name == "C3a":
+        P, _W, _H, sig = sc.CONFIGS["C3"]
+        cam = sc.make_camera(1920, 1088)
+        return sc, cam, sc.make_scene(P, cam, sig, seed=0, backdrop=True)
+    cam, scene = sc.config(name)
+    return sc, cam, scene
+
+
+@pytest.mark.parametrize("name,variant,track_off,map_off", TIMED)
+def test_timed_configs_match_reference_build_live(built, name, variant, track_off, map_off):
+    ref = ge.load_reference(variant)
+    if ref is None:
+        pytest.skip("baseline/_ref not present on this box")
+    sc, cam, scene = _timed_case(name)
+    cot = sc.make_cotangents(cam, _n_aux(variant))
+    mod = built.load_variant(variant)
+    o_m, g_m = pu.run_variant(mod, variant, cam, scene, cot, track_off=track_off, map_off=map_off)
+    torch.cuda.empty_cache()
+    o_r, g_r = pu.run_variant(ref, variant, cam, scene, cot, track_off=track_off, map_off=map_off)
+    torch.cuda.empty_cache()
+    if variant == "full" and name != "C3a":
+        g_m.pop("viewmatrix"), g_r.pop("viewmatrix")
+    stats = {}
+    ok, lines = pu.compare_runs(o_m, g_m, o_r, g_r, grad_budget=1e-3, strict=True, stats=stats)
+    print("%s -%s track_off=%s map_off=%s: %s" % (name, variant, track_off, map_off, stats))
+    assert ok, "\n".join(lines)
+    assert np.array_equal(o_m["color"], o_r["color"]) and np.array_equal(o_m["depth"], o_r["depth"])
 
 
 # ---- straight through the C ABI (no torch shim) ------------------------------------------------
@@ -241,9 +285,73 @@ def test_c_abi_light_forward_backward_matches_oracle(built):
     torch.cuda.synchronize()
     for ours, key in ((g["m3"], "means3D"), (g["sh"], "shs"), (g["scl"], "scales"), (g["rot"], "rotations")):
         rel, bad = pu.grad_mismatch(ours.cpu().numpy().reshape(o_grads[key].shape), o_grads[key])
-        assert rel < 5e-3 and bad < 1e-2, key
+        assert rel < 1e-3 and bad < 1e-2, (key, rel, bad)
     rel, _ = pu.grad_mismatch(g["view"].cpu().numpy().reshape(4, 4), o_grads["viewmatrix"])
     assert rel < 1e-3
+
+
+def test_c_abi_full_forward_backward_matches_oracle(built):
+    """-full entry points straight through the C ABI (no torch shim): gsr_full_forward /
+    gsr_full_backward on a 16-aligned, fully covered image so that dL/dviewmatrix is comparable."""
+    sc, cam, scene = _scene(1200, 96, 64, seed=33, backdrop=True)
+    cot = sc.make_cotangents(cam, 2)
+    lib = ctypes.CDLL(built.core_library_path())
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    lib.gsr_backward_scratch_floats.restype = ctypes.c_size_t
+    P, M, W, H = scene.means3D.shape[0], 16, cam.W, cam.H
+    d = lambda t: t.to(DEV).contiguous()
+    t_in = dict(bg=d(scene.bg), means=d(scene.means3D), shs=d(scene.shs), op=d(scene.opacities),
+                sc=d(scene.scales), rot=d(scene.rotations), view=d(cam.viewmatrix),
+                proj=d(cam.projmatrix), campos=d(cam.campos), gt=d(scene.gt_depth),
+                persp=d(cam.perspec_matrix))
+    bufs = {}
+
+    def make_alloc(tag):
+        def cb(_ctx, nbytes):
+            bufs[tag] = torch.empty(max(int(nbytes), 1) + 256, dtype=torch.uint8, device=DEV)
+            return (bufs[tag].data_ptr() + 255) // 256 * 256
+        return ALLOC_FN(cb)
+    a_geom, a_bin, a_img = make_alloc("geom"), make_alloc("bin"), make_alloc("img")
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=DEV)
+    color, depth, unc = f(3, H, W), f(H, W), f(H, W)
+    radii = torch.empty(P, dtype=torch.int32, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    nr, ng = ctypes.c_int(0), ctypes.c_int(0)
+    cf = ctypes.c_float
+    rc = lib.gsr_full_forward(
+        a_geom, None, a_bin, None, a_img, None, P, 3, M, p(t_in["bg"]), W, H, p(t_in["means"]),
+        p(t_in["shs"]), None, p(t_in["op"]), p(t_in["sc"]), cf(1.0), p(t_in["rot"]), None,
+        p(t_in["view"]), p(t_in["proj"]), p(t_in["campos"]), cf(cam.tanfovx), cf(cam.tanfovy), 0,
+        p(color), p(depth), p(unc), p(radii), p(t_in["gt"]), None, ctypes.byref(nr), ctypes.byref(ng))
+    assert rc == 0, lib.gsr_last_error()
+    torch.cuda.synchronize()
+    o_outs, o_grads = pu.run_oracle("full", cam, scene, cot)
+    assert 0 < nr.value <= o_outs["_num_rendered"]
+    assert (radii.cpu().numpy() == o_outs["radii"]).all()
+    assert pu.image_mismatch(color.cpu().numpy(), o_outs["color"])[0] <= 4
+    assert pu.image_mismatch(depth.cpu().numpy()[None], o_outs["depth"])[0] <= 4
+    assert pu.image_mismatch(unc.cpu().numpy()[None], o_outs["uncertainty"])[0] <= 4
+
+    gc, gd, gu = d(cot[0]), d(cot[1][0]), d(cot[1][1])
+    g = dict(m2=f(P, 3), conic=f(P, 4), opac=f(P), col=f(P, 3), dep=f(P), m3=f(P, 3), cov=f(P, 6),
+             sh=f(P, M, 3), scl=f(P, 3), rot=f(P, 4), view=f(16))
+    scratch = f(lib.gsr_backward_scratch_floats(P))
+    al = lambda tag: ctypes.c_void_p((bufs[tag].data_ptr() + 255) // 256 * 256)
+    rc = lib.gsr_full_backward(
+        P, 3, M, nr.value, p(t_in["bg"]), W, H, p(t_in["means"]), p(t_in["shs"]), None,
+        p(t_in["sc"]), cf(1.0), p(t_in["rot"]), None, p(t_in["view"]), p(t_in["proj"]),
+        p(t_in["campos"]), cf(cam.tanfovx), cf(cam.tanfovy), p(radii), al("geom"), al("bin"), al("img"),
+        p(gc), p(gd), p(gu), p(g["m2"]), p(g["conic"]), p(g["opac"]), p(g["col"]), p(g["dep"]),
+        p(g["m3"]), p(g["cov"]), p(g["sh"]), p(g["scl"]), p(g["rot"]), p(t_in["persp"]), p(g["view"]),
+        p(t_in["gt"]), p(scratch), None, None)
+    assert rc == 0, lib.gsr_last_error()
+    torch.cuda.synchronize()
+    for ours, key in ((g["m3"], "means3D"), (g["sh"], "shs"), (g["scl"], "scales"), (g["rot"], "rotations"),
+                      (g["opac"], "opacities")):
+        rel, bad = pu.grad_mismatch(ours.cpu().numpy().reshape(o_grads[key].shape), o_grads[key])
+        assert rel < 1e-3 and bad < 1e-2, (key, rel, bad)
+    rel, _ = pu.grad_mismatch(g["view"].cpu().numpy().reshape(4, 4), o_grads["viewmatrix"])
+    assert rel < 1e-3, rel
 
 
 def test_c_abi_reports_errors(built):

@@ -18,4 +18,10 @@ for variant in ("light", "full"):
         pu.set_option("tile_sort", 0)
         pu.run_variant(mod, variant, cam, scene, cot)
         pu.set_option("tile_sort", 1)
-print("done")
+print("rasterizer done")
+# the device-side tracker (CUDA graph of 8 kernels + memset, fused loss, on-chip pose update)
+import test_tracking_gpu as tt
+s = tt._setup(P=3000, W=160, H=96)
+t = tt._tracker(s, max_iterations=8)
+r = t.run(4)
+print("tracker done", r["loss"])
