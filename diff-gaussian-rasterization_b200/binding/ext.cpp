@@ -10,10 +10,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mark_visible", &markVisible);
   // extension (not in the reference): flat scene-gradient arena for view-level data parallelism
   m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false);
+  m.def("arm_grad_arena", &armGradArena);
   m.def("sh_grad_from_views", &shGradFromViews);
   // extensions for the NVLS exchange of dp.py (mode "nvls"): P2P-reading SH rebuild, in-switch slice all-reduce
   m.def("sh_grad_from_view_ptrs", &shGradFromViewPtrs);
-  m.def("nvls_allreduce_slice", &nvlsAllreduceSlice);
+  m.def("nvls_allreduce_slice", &nvlsAllreduceSlice, pybind11::arg("multicast_ptr"), pybind11::arg("offset_floats"),
+        pybind11::arg("count_floats"), pybind11::arg("rank"), pybind11::arg("world"), pybind11::arg("max_blocks") = 0);
   // extension (not in the reference): in-kernel densification statistics
   m.def("set_densify_stats", &setDensifyStats, pybind11::arg("grad_accum"), pybind11::arg("denom"),
         pybind11::arg("max_radii2D"));

@@ -29,7 +29,11 @@ torch::Tensor prep(const torch::Tensor& t, const torch::Device& dev, const char*
   if (!t.defined() || t.numel() == 0) return torch::Tensor();
   TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
   TORCH_CHECK(t.device() == dev, name, " must live on ", dev, " (got ", t.device(), ")");
-  return t.contiguous();
+  torch::Tensor c = t.contiguous();
+  // the core reads rotations / SH rows with 128-bit loads: a contiguous view at a storage offset
+  // that is not a multiple of 16 bytes is re-packed (fresh allocations are always aligned)
+  if ((reinterpret_cast<uintptr_t>(c.data_ptr()) & 15) != 0) c = c.clone();
+  return c;
 }
 
 const float* fptr(const torch::Tensor& t) {
@@ -48,6 +52,7 @@ torch::Tensor scratch_for(int P, const torch::TensorOptions& fopts) {
 }
 
 torch::Tensor g_grad_arena;  // see setGradArena
+bool g_arena_armed = false;  // the arena takes the NEXT backward only (one-shot), see armGradArena
 torch::Tensor g_densify_accum, g_densify_denom, g_max_radii;  // see setDensifyStats
 bool g_arena_factorized = false;
 
@@ -70,7 +75,11 @@ void fill_densify(gsr_backward_extras& ex, int P, const torch::Tensor& like) {
 // the five scene-parameter gradients: views of the registered arena when it fits, fresh tensors otherwise
 SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torch::TensorOptions& fopts) {
   SceneGrads g;
-  const bool arena_ok = g_grad_arena.defined() && g_grad_arena.device() == like.device() &&
+  // One-shot: the arena is OVERWRITTEN, not accumulated into, so it may only take one backward per
+  // exchange.  A further backward before the arena is re-armed (several views per rank, a tracking
+  // pass on the same scene) gets fresh tensors and autograd adds them to .grad as usual.
+  const bool armed = g_arena_armed;
+  const bool arena_ok = armed && g_grad_arena.defined() && g_grad_arena.device() == like.device() &&
                         g_grad_arena.scalar_type() == torch::kFloat32 && g_grad_arena.is_contiguous() &&
                         P > 0 && P % 4 == 0;
   if (arena_ok && g_arena_factorized && M > 0 && g_grad_arena.numel() == (int64_t)P * 14 + 4) {
@@ -87,10 +96,11 @@ SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torc
     g.opacity = take((int64_t)P, {P, 1});
     g.scales = take((int64_t)P * 3, {P, 3});
     g.rotations = take((int64_t)P * 4, {P, 4});
+    g_arena_armed = false;
     return g;  // g.sh stays undefined: dL_dsh is not written in this mode
   }
   const int64_t need = (int64_t)P * (3 + 3 * (int64_t)M + 1 + 3 + 4);
-  if (!g_arena_factorized && g_grad_arena.defined() && g_grad_arena.numel() == need && g_grad_arena.device() == like.device() &&
+  if (armed && !g_arena_factorized && g_grad_arena.defined() && g_grad_arena.numel() == need && g_grad_arena.device() == like.device() &&
       g_grad_arena.scalar_type() == torch::kFloat32 && g_grad_arena.is_contiguous() && P > 0 &&
       P % 4 == 0 /* keeps every slice 16-byte aligned for the kernels' 128-bit stores */) {
     int64_t off = 0;
@@ -104,6 +114,7 @@ SceneGrads alloc_scene_grads(int P, int M, const torch::Tensor& like, const torc
     g.opacity = take((int64_t)P, {P, 1});
     g.scales = take((int64_t)P * 3, {P, 3});
     g.rotations = take((int64_t)P * 4, {P, 4});
+    g_arena_armed = false;
   } else {
     g.means3D = torch::empty({P, 3}, fopts);
     g.sh = torch::empty({P, M, 3}, fopts);
@@ -410,12 +421,21 @@ void setGradArena(const torch::Tensor& arena, bool factorized_sh) {
   if (!arena.defined() || arena.numel() == 0) {
     g_grad_arena = torch::Tensor();
     g_arena_factorized = false;
+    g_arena_armed = false;
     return;
   }
   TORCH_CHECK(arena.is_cuda() && arena.scalar_type() == torch::kFloat32 && arena.is_contiguous() &&
                   arena.dim() == 1,
               "grad arena must be a contiguous 1-D float32 CUDA tensor");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(arena.data_ptr()) & 15) == 0,
+              "grad arena must be 16-byte aligned (the kernels write it with 128-bit stores)");
   g_grad_arena = arena;
+  g_arena_armed = true;
+}
+
+bool armGradArena() {
+  g_arena_armed = g_grad_arena.defined();
+  return g_arena_armed;
 }
 
 torch::Tensor shGradFromViews(const torch::Tensor& means3D, const torch::Tensor& gathered, const int degree,
@@ -455,9 +475,9 @@ torch::Tensor shGradFromViewPtrs(const torch::Tensor& means3D, const std::vector
 }
 
 void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t count_floats, int64_t rank,
-                        int64_t world) {
+                        int64_t world, int64_t max_blocks) {
   const int rc = gsr_nvls_allreduce_slice(reinterpret_cast<float*>(multicast_ptr), (size_t)offset_floats,
-                                          (size_t)count_floats, (int)rank, (int)world,
+                                          (size_t)count_floats, (int)rank, (int)world, (int)max_blocks,
                                           at::cuda::getCurrentCUDAStream().stream());
   check_rc(rc, "gsr_nvls_allreduce_slice");
 }

@@ -79,11 +79,17 @@ RasterizeGaussiansBackwardCUDA(
 // (14P + 4 floats): the backward then writes the masked colour gradient and the camera position
 // instead of dL_dsh (whose returned tensor is undefined / None); the summed dL_dsh of all views is
 // rebuilt with shGradFromViews after an all-gather of the first 3P + 4 floats.
+// The arena is ONE-SHOT: registering arms it, the next backward that fits writes into it and disarms
+// it, armGradArena() re-arms it (dp.SceneGradReducer does so after every exchange).  Backwards that
+// run while it is disarmed return fresh tensors, which autograd accumulates into .grad as usual — so
+// several backwards per exchange (several views per rank, a tracking pass on the same scene) add up
+// instead of clobbering each other.
 void setGradArena(const torch::Tensor& arena, bool factorized_sh);
+bool armGradArena();
 torch::Tensor shGradFromViewPtrs(const torch::Tensor& means3D, const std::vector<int64_t>& dR_ptrs,
                                  const std::vector<int64_t>& campos_ptrs, const int degree, const int M);
 void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t count_floats, int64_t rank,
-                        int64_t world);
+                        int64_t world, int64_t max_blocks);
 void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom,
                      const torch::Tensor& max_radii2D);
 

@@ -72,7 +72,7 @@ def build_core(force=False):
         list(ex.map(_run, jobs))
     lib = core_lib_path()
     if force or jobs or _newer(lib, objs):
-        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-ldl"])
     return lib
 
 
@@ -103,7 +103,8 @@ def build_shim(variant, force=False):
     _run([CXX, "-shared", "-o", out] + objs +
          ["-L" + LIBDIR, "-lgsr_b200", "-L" + torch_lib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda",
           "-lc10", "-lc10_cuda", "-ltorch_python",
-          "-Wl,-rpath,$ORIGIN/../../lib", "-Wl,-rpath," + torch_lib])
+          # in-tree: the core sits in ../../lib; pip-installed (light|full/setup.py): next to the shim
+          "-Wl,-rpath,$ORIGIN:$ORIGIN/../../lib", "-Wl,-rpath," + torch_lib, "-ldl"])
     return out
 
 

@@ -9,13 +9,22 @@
 #include <utility>
 #include <vector>
 
+#include <atomic>
+
+#include <nvtx3/nvToolsExt.h>
+
 #include "gsr_common.cuh"
 
 namespace gsr {
 
 namespace {
 thread_local char g_err[512] = "";
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_prefetch=*/0};
+std::atomic<long long> g_launches{0};
+// Process-wide defaults (gsr_set_option).  Every entry point takes a thread-local SNAPSHOT of them
+// when it starts (OptionsCall), and everything below reads the snapshot: a concurrent
+// gsr_set_option from another thread can never change the switches in the middle of a call, and a
+// value one thread's call is using is never written by another thread.
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -68,16 +77,28 @@ StageTimer& stage_timer() {
 const char* const kStageNames[ST_COUNT] = {"preprocess_fwd", "scan", "emit_keys", "radix_sort",
                                            "tile_ranges", "render_fwd", "render_bwd",
                                            "preprocess_bwd", "memset", "other"};
+thread_local Options t_opts = g_opts;
 }  // namespace
 
+// Every stage is an NVTX range (visible in Nsight Systems / ncu --nvtx) and, with the
+// "stage_timing" option, a CUDA-event pair on the launching stream.
 StageScope::StageScope(int stage, cudaStream_t s, int nlaunch) : slot(-1), stream(s) {
-  if (g_opts.stage_timing) slot = stage_timer().begin(stage, nlaunch, s);
+  nvtxRangePushA(kStageNames[stage]);
+  g_launches.fetch_add(nlaunch, std::memory_order_relaxed);
+  if (t_opts.stage_timing) slot = stage_timer().begin(stage, nlaunch, s);
 }
 StageScope::~StageScope() {
   if (slot >= 0) stage_timer().end(slot, stream);
+  nvtxRangePop();
 }
 
-Options& options() { return g_opts; }
+Options& options() { return t_opts; }
+
+OptionsCall::OptionsCall(const char* entry_point) {
+  t_opts = g_opts;
+  nvtxRangePushA(entry_point);
+}
+OptionsCall::~OptionsCall() { nvtxRangePop(); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -122,6 +143,21 @@ int check_common(const char* who, int P, int width, int height, const float* mea
   }
   if (!cov3D_precomp && (!scales || !rotations)) {
     set_error("%s: provide scales+rotations or a precomputed 3D covariance", who);
+    return GSR_E_INVALID;
+  }
+  if (!cov3D_precomp && (reinterpret_cast<uintptr_t>(rotations) & 15) != 0) {
+    set_error("%s: rotations must be 16-byte aligned (read with 128-bit loads)", who);
+    return GSR_E_INVALID;
+  }
+  return GSR_OK;
+}
+
+// 128-bit stores of the per-Gaussian backward
+int check_grad_alignment(const char* who, const float* rotations, const float* cov3D_precomp,
+                         const float* dL_dconic, const float* dL_drot) {
+  if ((reinterpret_cast<uintptr_t>(dL_dconic) & 15) != 0 || (reinterpret_cast<uintptr_t>(dL_drot) & 15) != 0 ||
+      (!cov3D_precomp && (reinterpret_cast<uintptr_t>(rotations) & 15) != 0)) {
+    set_error("%s: rotations, dL_dconic and dL_drot must be 16-byte aligned (128-bit accesses)", who);
     return GSR_E_INVALID;
   }
   return GSR_OK;
@@ -214,7 +250,6 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "track_headroom_pct")) return &g_opts.track_headroom_pct;
   if (!strcmp(key, "bulk_sh")) return &g_opts.bulk_sh;
   if (!strcmp(key, "cnt_stride")) return &g_opts.cnt_stride;
-  if (!strcmp(key, "bwd_prefetch")) return &g_opts.bwd_prefetch;
   return nullptr;
 }
 
@@ -230,6 +265,10 @@ int gsr_get_option(const char* key) {
   int* s = option_slot(key);
   if (!s) { set_error("unknown option '%s'", key ? key : "(null)"); return GSR_E_INVALID; }
   return *s;
+}
+
+long long gsr_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int gsr_stage_times(double* ms, long long* scopes, long long* launches, int reset) {
@@ -260,6 +299,7 @@ int gsr_light_forward(
     float* out_depth_var, float* gau_uncertainty, int* gau_related_pixels, int* radii, int debug,
     void* stream, int* num_rendered) {
   g_err[0] = 0;
+  OptionsCall oc("gsr_light_forward");
   int rc = check_common("gsr_light_forward", P, width, height, means3D, shs, colors_precomp, scales,
                         rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos);
   if (rc != GSR_OK) return rc;
@@ -307,6 +347,7 @@ int gsr_full_forward(
     float* out_depth, float* out_uncertainty, int* radii, const float* gt_depth, void* stream,
     int* num_rendered, int* num_related) {
   g_err[0] = 0;
+  OptionsCall oc("gsr_full_forward");
   (void)gt_depth;  // loaded but unused by the reference's forward (forward.cu:313-317)
   int rc = check_common("gsr_full_forward", P, width, height, means3D, shs, colors_precomp, scales,
                         rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos);
@@ -359,6 +400,7 @@ int gsr_light_backward(
     const float* perspec_matrix, float* dL_dview, const float* gt_depth, int track_off,
     int map_off, float* scratch, void* stream, const gsr_backward_extras* extras) {
   g_err[0] = 0;
+  OptionsCall oc("gsr_light_backward");
   (void)colors_precomp;  // colours come from the packed record written by the forward
   cudaStream_t s = (cudaStream_t)stream;
   if (!dL_dview) { set_error("gsr_light_backward: dL_dview is NULL"); return GSR_E_INVALID; }
@@ -374,7 +416,9 @@ int gsr_light_backward(
   }
   Camera cam = make_camera(viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, width, height);
   GeomState g; BinState b; ImgState img;
-  int rc = rederive(kLight, P, R, width, height, geom_buffer, binning_buffer, img_buffer, g, b, img, cam);
+  int rc = check_grad_alignment("gsr_light_backward", rotations, cov3D_precomp, dL_dconic, dL_drot);
+  if (rc != GSR_OK) return rc;
+  rc = rederive(kLight, P, R, width, height, geom_buffer, binning_buffer, img_buffer, g, b, img, cam);
   if (rc != GSR_OK) return rc;
   float* acc = scratch;
   float* partials = scratch + (size_t)P * kAccStride;
@@ -417,6 +461,7 @@ int gsr_full_backward(
     const float* perspec_matrix, float* dL_dview, const float* gt_depth, float* scratch,
     void* stream, const gsr_backward_extras* extras) {
   g_err[0] = 0;
+  OptionsCall oc("gsr_full_backward");
   (void)colors_precomp;
   cudaStream_t s = (cudaStream_t)stream;
   if (!dL_dview) { set_error("gsr_full_backward: dL_dview is NULL"); return GSR_E_INVALID; }
@@ -431,7 +476,9 @@ int gsr_full_backward(
   }
   Camera cam = make_camera(viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, width, height);
   GeomState g; BinState b; ImgState img;
-  int rc = rederive(kFull, P, R, width, height, geom_buffer, binning_buffer, img_buffer, g, b, img, cam);
+  int rc = check_grad_alignment("gsr_full_backward", rotations, cov3D_precomp, dL_dconic, dL_drot);
+  if (rc != GSR_OK) return rc;
+  rc = rederive(kFull, P, R, width, height, geom_buffer, binning_buffer, img_buffer, g, b, img, cam);
   if (rc != GSR_OK) return rc;
   float* acc = scratch;
   float* partials = scratch + (size_t)P * kAccStride;

@@ -11,6 +11,7 @@
 // Roofline: HBM. Algorithmic bytes: scan 8*P; emit 20*P + 12*N; sort (24*passes + 8)*N;
 // ranges 8*N + 8*tiles.
 #include <atomic>
+#include <mutex>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -392,17 +393,18 @@ sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__
   }
 }
 
-// Pinned read-back slots for the duplicate count (so the copy is truly asynchronous) and the
-// sizes seen on the previous frame (to size this frame's binning buffer before the count is known).
-struct CountSlots {
+// Per-DEVICE read-back resources: pinned slots for the duplicate count (so the copy is truly
+// asynchronous), their events (events belong to the device they were created on) and the one-time
+// kernel attribute of sort_tiles_kernel.  Created lazily for the device that is current at the call.
+struct DeviceSlots {
   static constexpr int kSlots = 32;
   uint32_t* host = nullptr;  // [kSlots][4] pinned
   cudaEvent_t ev[kSlots];
   std::atomic<unsigned> next{0};
-  std::atomic<uint32_t> hint_entries{0}, hint_longest{0};
   bool ok = false;
-  CountSlots() {
-    if (cudaHostAlloc(reinterpret_cast<void**>(&host), sizeof(uint32_t) * 4 * kSlots, cudaHostAllocDefault) != cudaSuccess) {
+  bool sort_attr_set = false;
+  void init() {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host), sizeof(uint32_t) * 4 * kSlots, cudaHostAllocPortable) != cudaSuccess) {
       cudaGetLastError();
       return;
     }
@@ -411,9 +413,80 @@ struct CountSlots {
     ok = true;
   }
 };
-CountSlots& count_slots() {
-  static CountSlots* s = new CountSlots();  // leaked on purpose (outlives static destruction)
-  return *s;
+constexpr int kMaxDevices = 64;
+std::mutex g_ctx_mu;
+DeviceSlots* g_dev_slots[kMaxDevices] = {nullptr};
+
+DeviceSlots* device_slots(int* device_out = nullptr) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (device_out) *device_out = dev;
+  if (dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (g_dev_slots[dev] == nullptr) {
+    g_dev_slots[dev] = new DeviceSlots();  // leaked on purpose (outlives static destruction)
+    g_dev_slots[dev]->init();
+  }
+  return g_dev_slots[dev];
+}
+
+// Speculative-binning size estimate, one per (device, width, height, P) context: the sizes seen on
+// that context's previous frame size this frame's binning buffer before the count is known.  A
+// context speculates only while its estimate is `stable` (the last frame's counts would have fitted
+// the estimate made from the frame before), so an alternating or drifting workload falls back to the
+// synchronous path instead of mis-speculating every frame.
+struct BinContext {
+  int device, W, H, P;
+  uint32_t hint_entries, hint_longest;
+  bool stable;
+  uint64_t stamp;
+};
+constexpr int kMaxContexts = 64;
+BinContext g_ctx[kMaxContexts];
+int g_ctx_n = 0;
+uint64_t g_ctx_clock = 0;
+
+uint32_t spec_capacity(uint32_t hint_n) { return hint_n + hint_n / 4 + 4096; }
+uint32_t spec_longest(uint32_t hint_l) {
+  uint32_t l = hint_l * 2 < (uint32_t)kTileSortThreads ? (uint32_t)kTileSortThreads : hint_l * 2;
+  return l > (uint32_t)kTileSortCap ? (uint32_t)kTileSortCap : l;
+}
+
+// -> true and the estimate when this context may speculate
+bool context_hint(int device, int W, int H, int P, uint32_t* n, uint32_t* l) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  for (int i = 0; i < g_ctx_n; ++i) {
+    BinContext& c = g_ctx[i];
+    if (c.device == device && c.W == W && c.H == H && c.P == P) {
+      c.stamp = ++g_ctx_clock;
+      *n = c.hint_entries; *l = c.hint_longest;
+      return c.stable && c.hint_entries > 0 && c.hint_longest <= (uint32_t)kTileSortCap;
+    }
+  }
+  return false;
+}
+
+void context_update(int device, int W, int H, int P, uint32_t n, uint32_t l) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  BinContext* c = nullptr;
+  for (int i = 0; i < g_ctx_n; ++i)
+    if (g_ctx[i].device == device && g_ctx[i].W == W && g_ctx[i].H == H && g_ctx[i].P == P) c = &g_ctx[i];
+  if (c == nullptr) {
+    if (g_ctx_n < kMaxContexts) {
+      c = &g_ctx[g_ctx_n++];
+    } else {  // evict the least recently used context
+      c = &g_ctx[0];
+      for (int i = 1; i < g_ctx_n; ++i) if (g_ctx[i].stamp < c->stamp) c = &g_ctx[i];
+    }
+    *c = BinContext{device, W, H, P, n, l, /*stable=*/true, ++g_ctx_clock};
+    return;
+  }
+  int p = kTileSortThreads;
+  while (p < (int)spec_longest(c->hint_longest)) p <<= 1;
+  c->stable = c->hint_entries > 0 && n <= spec_capacity(c->hint_entries) && l <= (uint32_t)p;
+  c->hint_entries = n;
+  c->hint_longest = l;
+  c->stamp = ++g_ctx_clock;
 }
 
 int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgState& img, BinState& b,
@@ -431,11 +504,12 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
     int p = kTileSortThreads;  // the register network exchanges 256*E entries through smem
     while (p < (int)longest_cap) p <<= 1;
     const size_t smem = (size_t)p * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (and only needed for long lists)
+    DeviceSlots* ds = smem > 48 * 1024 ? device_slots() : nullptr;
+    if (smem > 48 * 1024 && (ds == nullptr || !ds->sort_attr_set)) {
       GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kTileSortCap * (int)sizeof(uint64_t)));
-      attr_set = true;
+      if (ds != nullptr) ds->sort_attr_set = true;
     }
     sort_tiles_kernel<<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals,
                                                                 capacity, p);
@@ -493,20 +567,23 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     // pinned memory asynchronously and — when a previous frame left a size estimate — the scatter
     // and the per-tile sort are enqueued first, on a buffer sized from that estimate; the kernels
     // are guarded, and if the estimate turns out too small the binning is simply redone.
-    CountSlots& cs = count_slots();
-    const uint32_t hint_n = cs.hint_entries.load(), hint_l = cs.hint_longest.load();
-    const bool speculate = cs.ok && options().async_binning != 0 && hint_n > 0 && hint_l <= (uint32_t)kTileSortCap;
+    int device = 0;
+    DeviceSlots* dsp = device_slots(&device);
+    const bool slots_ok = dsp != nullptr && dsp->ok;
+    uint32_t hint_n = 0, hint_l = 0;
+    const bool speculate = slots_ok && options().async_binning != 0 &&
+                           context_hint(device, cam.W, cam.H, P, &hint_n, &hint_l);
     uint32_t h[4] = {0, 0, 0, 0};
-    if (cs.ok) {
-      const unsigned slot = cs.next.fetch_add(1) % CountSlots::kSlots;
+    if (slots_ok) {
+      DeviceSlots& cs = *dsp;
+      const unsigned slot = cs.next.fetch_add(1) % DeviceSlots::kSlots;
       uint32_t* hp = cs.host + 4 * slot;
       GSR_CUDA_OK(cudaMemcpyAsync(hp, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
       GSR_CUDA_OK(cudaEventRecord(cs.ev[slot], stream));
       uint32_t cap = 0, lcap = 0;
       if (speculate) {
-        cap = hint_n + hint_n / 4 + 4096;
-        lcap = hint_l * 2 < (uint32_t)kTileSortThreads ? (uint32_t)kTileSortThreads : hint_l * 2;
-        if (lcap > (uint32_t)kTileSortCap) lcap = kTileSortCap;
+        cap = spec_capacity(hint_n);
+        lcap = spec_longest(hint_l);
         const size_t need = BinState::carve(b, nullptr, cap, 0, false);
         char* chunk = alloc(alloc_ctx, need);
         if (chunk == nullptr) { set_error("binning allocator returned NULL for %zu bytes", need); return GSR_E_ALLOC; }
@@ -534,8 +611,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     }
     N = h[0];
     longest = h[2];
-    cs.hint_entries.store(N);
-    cs.hint_longest.store(longest);
+    context_update(device, cam.W, cam.H, P, N, longest);
   } else {
     StageScope st(ST_SCAN, stream);
     GSR_CUDA_OK(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_bytes, g.tiles_touched,

@@ -52,9 +52,14 @@ struct Options {
   int track_headroom_pct;
   int bulk_sh;
   int cnt_stride;
-  int bwd_prefetch;
 };
-Options& options();
+Options& options();  // the calling thread's snapshot (see OptionsCall)
+// RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the
+// calling thread's snapshot and opens an NVTX range named after the entry point.
+struct OptionsCall {
+  explicit OptionsCall(const char* entry_point);
+  ~OptionsCall();
+};
 inline int cnt_stride() { const int s = options().cnt_stride; return (s >= 1 && s <= kCntStrideMax) ? s : 1; }
 
 // ---- stage timing (gsr_stage_times in the C ABI) ---------------------------------------------

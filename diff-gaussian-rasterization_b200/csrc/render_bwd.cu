@@ -339,19 +339,7 @@ __device__ __forceinline__ unsigned block_mask4(const float4& r0, const float4& 
   return mask;
 }
 
-// PREFETCH (option "bwd_prefetch", default off until timed on the GPU): the gather of the NEXT
-// round's records runs as cp.async copies underneath the current round's walk instead of in front of
-// it (the ncu source page shows 8.5 % of the kernel's samples as barrier stalls at the staging step).
-// Every thread owns one raw slot: it converts its landed record into the duplicated layout, then
-// re-issues the copies for the following round into the same slot; the list index is fetched two
-// rounds ahead into a register.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int VARIANT, bool POSE_ONLY, bool PREFETCH>
+template <int VARIANT, bool POSE_ONLY>
 __global__ void __launch_bounds__(kBwd2Threads, 8)
 render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                    const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
@@ -368,7 +356,6 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   // staged entry, duplicated into pairs: q0 = (xg, pc | yg, yg)  q1 = (A, A | -B, -B)
   //   q2 = (C, C | o, o)  q3 = (depth, depth | r, r)  q4 = (g, g | b, b)
   __shared__ ulonglong2 s_q[5][kBwd2Batch];  // one array: an entry's five vectors are constant offsets apart
-  __shared__ float4 s_raw[PREFETCH ? 3 : 1][PREFETCH ? kBwd2Batch : 1];  // landing slots of the next round's records
   __shared__ int s_id[kBwd2Batch];
   __shared__ unsigned char s_mask[kBwd2Batch];
   __shared__ unsigned char s_list[kBwd2Warps][kBwd2Batch];
@@ -425,41 +412,13 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   const unsigned red_st = smem_u32(&s_red[0][tid]);
   const unsigned red_ld = smem_u32(&s_red[(lane >> 1) % kRedVals][(tid & ~31) + (lane & 1) * 16]);
 
-  // PREFETCH: list index of this thread's entry in the round being fetched / the one after it
-  auto entry_id = [&](int round) -> int {
-    const int p = round * kBwd2Batch + tid;
-    return p < walk ? (int)point_list[range.x + (walk - p - 1)] : -1;
-  };
-  auto fetch = [&](int id) {   // start the copies of one record into this thread's raw slot
-    if (id >= 0) {
-      const float4* r = rec + 3 * (size_t)id;
-      cp_async16(&s_raw[0][tid], r + 0);
-      cp_async16(&s_raw[PREFETCH ? 1 : 0][tid], r + 1);
-      cp_async16(&s_raw[PREFETCH ? 2 : 0][tid], r + 2);
-    }
-    cp_async_commit();
-  };
-  int id_cur = -1, id_nxt = -1;
-  if (PREFETCH) {
-    id_cur = entry_id(0);
-    id_nxt = entry_id(1);
-    fetch(id_cur);
-  }
-
   for (int i = 0; i < rounds; ++i) {
-    if (PREFETCH) cp_async_wait_all();   // this thread's record of round i has landed in its raw slot
     __syncthreads();
     const int progress = i * kBwd2Batch + tid;
     unsigned my_mask = 0u;
     float4 q0, q1, q2;
     int id = -1;
-    if (PREFETCH) {
-      id = id_cur;
-      if (id >= 0) { q0 = s_raw[0][tid]; q1 = s_raw[PREFETCH ? 1 : 0][tid]; q2 = s_raw[PREFETCH ? 2 : 0][tid]; }
-      fetch(id_nxt);                     // next round's record, underneath this round's walk
-      id_cur = id_nxt;
-      id_nxt = entry_id(i + 2);
-    } else if (progress < walk) {
+    if (progress < walk) {
       id = (int)point_list[range.x + (walk - progress - 1)];
       const float4* r = rec + 3 * (size_t)id;
       q0 = __ldg(r + 0); q1 = __ldg(r + 1); q2 = __ldg(r + 2);
@@ -613,20 +572,16 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
       img.n_contrib, FC, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar, acc
   if (variant == kLight) {
     if (packed && pose_only)
-      render_bwd2_kernel<kLight, true, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
-    else if (packed && options().bwd_prefetch != 0)
-      render_bwd2_kernel<kLight, false, true><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
+      render_bwd2_kernel<kLight, true><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
     else if (packed)
-      render_bwd2_kernel<kLight, false, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
+      render_bwd2_kernel<kLight, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
     else if (pose_only)
       render_bwd_kernel<kLight, true><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
     else
       render_bwd_kernel<kLight, false><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
   } else {
-    if (packed && options().bwd_prefetch != 0)
-      render_bwd2_kernel<kFull, false, true><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
-    else if (packed)
-      render_bwd2_kernel<kFull, false, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
+    if (packed)
+      render_bwd2_kernel<kFull, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
     else
       render_bwd_kernel<kFull, false><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
   }

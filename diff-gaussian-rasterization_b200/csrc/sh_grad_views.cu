@@ -259,7 +259,7 @@ extern "C" int gsr_sh_grad_from_view_ptrs(int P, int D, int M, const float* mean
 }
 
 extern "C" int gsr_nvls_allreduce_slice(float* multicast_ptr, size_t offset_floats, size_t count_floats,
-                                        int rank, int world, void* stream) {
+                                        int rank, int world, int max_blocks, void* stream) {
   using namespace gsr;
   if (!multicast_ptr || world <= 0 || rank < 0 || rank >= world || (offset_floats & 3) || (count_floats & 3) ||
       (reinterpret_cast<uintptr_t>(multicast_ptr) & 15)) {
@@ -274,7 +274,8 @@ extern "C" int gsr_nvls_allreduce_slice(float* multicast_ptr, size_t offset_floa
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = e4 - b4;
   const size_t want = (n + 256 * kNvlsUnroll - 1) / (256 * kNvlsUnroll);
-  const int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
   StageScope st(ST_OTHER, s);
   nvls_reduce_slice_kernel<<<blocks, 256, 0, s>>>(multicast_ptr, b4, e4);
   GSR_LAUNCH_OK(false, s);

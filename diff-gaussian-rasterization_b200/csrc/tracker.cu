@@ -205,6 +205,7 @@ struct gsr_tracker {
   int P = 0, D = 0, M = 0, W = 0, H = 0;
   float tanx = 0.f, tany = 0.f;
   cudaStream_t stream = nullptr;
+  cudaEvent_t caller_ev = nullptr;  // orders `stream` after the caller's stream (gsr_tracker_run)
   // borrowed device pointers
   const float *means3D = nullptr, *shs = nullptr, *colors = nullptr, *opac = nullptr, *scales = nullptr,
               *rots = nullptr, *cov3D = nullptr, *bg = nullptr, *gt_color = nullptr, *gt_depth = nullptr;
@@ -240,6 +241,7 @@ void tracker_free(gsr_tracker* t) {
   cudaFree(t->geom_buf); cudaFree(t->img_buf); cudaFree(t->bin_buf); cudaFree(t->radii);
   cudaFree(t->alpha); cudaFree(t->dL_dpix); cudaFree(t->dL_ddepth); cudaFree(t->loss_partials);
   cudaFree(t->scratch); cudaFree(t->cam); cudaFree(t->ps); cudaFree(t->loss_hist);
+  if (t->caller_ev) cudaEventDestroy(t->caller_ev);
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -322,6 +324,7 @@ gsr_tracker* gsr_tracker_create(int P, int D, int M, int width, int height, floa
   t->P = P; t->D = D; t->M = M; t->W = width; t->H = height; t->tanx = tan_fovx; t->tany = tan_fovy;
   t->max_hist = max_iterations;
   bool ok = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&t->caller_ev, cudaEventDisableTiming) == cudaSuccess;
   const int HW = width * height;
   Camera& c = t->camera;
   c.tan_fovx = tan_fovx; c.tan_fovy = tan_fovy;
@@ -406,14 +409,19 @@ int gsr_tracker_set_pose(gsr_tracker* t, const float* quat_wxyz, const float* tr
 }
 
 int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iterations,
-                    float* loss_history, gsr_track_result* result) {
+                    float* loss_history, gsr_track_result* result, void* caller_stream) {
   set_error("%s", "");
+  OptionsCall oc("gsr_tracker_run");
   if (!t || !params || iterations <= 0 || iterations > t->max_hist) {
     set_error("gsr_tracker_run: bad arguments (iterations must be in [1, max_iterations])");
     return GSR_E_INVALID;
   }
   if (!t->means3D || !t->gt_color) { set_error("gsr_tracker_run: scene / frame not set"); return GSR_E_INVALID; }
   cudaStream_t s = t->stream;
+  // order the private stream after the caller's: the borrowed scene / frame tensors are usually the
+  // output of asynchronous work on that stream (see the stream contract in gsr_b200.h)
+  GSR_CUDA_OK(cudaEventRecord(t->caller_ev, (cudaStream_t)caller_stream));
+  GSR_CUDA_OK(cudaStreamWaitEvent(s, t->caller_ev, 0));
   const int tiles = t->camera.grid_x * t->camera.grid_y;
   PoseState start;
   GSR_CUDA_OK(cudaMemcpyAsync(&start, t->ps, sizeof(start), cudaMemcpyDeviceToHost, s));

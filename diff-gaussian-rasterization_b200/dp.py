@@ -35,6 +35,10 @@ from collections import OrderedDict
 import torch
 import torch.distributed as dist
 
+# Exchange used by bench.py / callers that do not choose: our own kernels over NVSwitch when symmetric
+# memory + multicast are available (fastest at 4 and 8 GPUs), else the NCCL factorized path.
+DEFAULT_MODE = "nvls"
+
 PARAM_ORDER = ("means3D", "shs", "opacities", "scales", "rotations")
 FACT_ORDER = ("means3D", "opacities", "scales", "rotations")  # all-reduced part of the factorized layout
 
@@ -182,7 +186,10 @@ class SceneGradReducer:
         cur = torch.cuda.current_stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"])
+            # a chain of switch round trips, not bandwidth: a few CTAs are enough, and they leave the
+            # SMs to the P2P SH rebuild that runs next to it
+            C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"],
+                                   max(16, 256 // n["world"]))
         mark(2)
         self.sh_sum = C.sh_grad_from_view_ptrs(self.means3D.detach(), n["peers"],
                                                [p + 4 * 3 * self.P for p in n["peers"]], self.sh_degree, self.M)
@@ -225,8 +232,11 @@ class SceneGradReducer:
     def pack(self, grads, masked_color=None, campos=None):
         for k, (o, n, _shape) in self.slices.items():
             g = grads.get(k)
+            if g is not None and g.data_ptr() == self.flat.data_ptr() + 4 * o:
+                continue                                   # already in place
             self.flat[o:o + n].copy_(g.reshape(-1) if g is not None else 0)
-        if self.mode in ("factorized_sh", "nvls"):
+        if self.mode in ("factorized_sh", "nvls") and masked_color is not None:
+            # (with attach() the armed backward has already written the head of the buffer)
             self.flat[:3 * self.P].copy_(masked_color.reshape(-1))
             self.flat[3 * self.P:3 * self.P + 3].copy_(campos.reshape(-1)[:3])
 
@@ -273,11 +283,21 @@ class SceneGradReducer:
 
     def reduce_async(self, grads=None, masked_color=None, campos=None):
         """Pack (unless the gradients already live in the flat buffer, see attach()) and launch the
-        exchange.  Returns immediately on CUDA; call wait() before reading views()."""
+        exchange.  Returns immediately on CUDA; call wait() before reading views() AND before the
+        next backward (the re-armed arena is overwritten by it).
+
+        Several backwards per exchange (several views per rank, a tracking pass on the same scene)
+        are fine: the arena takes the first one, the others return fresh tensors that autograd adds
+        to .grad — in place into the arena when .grad aliases it, else they are packed here.  In the
+        factorized modes the first backward leaves no dL/dsh (it is rebuilt from the masked colour
+        gradients); the dL/dsh of any further backward arrives in grads["shs"] and is all-reduced and
+        added on top.  Parameters must enter the step with .grad = None (zero_grad's default): a
+        zero-filled .grad that aliases the arena would be added to itself by autograd."""
         if self.mode == "nvls" and self._attached is None:
             raise RuntimeError("nvls exchange needs attach() to a B200-native rasterizer package")
         if grads is not None and not (self._attached is not None and self._aliases_flat(grads)):
             self.pack(grads, masked_color, campos)
+        extra_sh = grads.get("shs") if (grads is not None and self.mode in ("factorized_sh", "nvls")) else None
         if self.is_cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
@@ -285,10 +305,24 @@ class SceneGradReducer:
                     self._nvls_exchange()
                 else:
                     self._exchange()
+                if extra_sh is not None:
+                    self._add_extra_sh(extra_sh)
                 self._done = torch.cuda.Event()
                 self._done.record(self.stream)
+            if self._attached is not None:
+                self._attached._C.arm_grad_arena()   # the next step's first backward takes the arena again
         else:
             self._exchange()
+            if extra_sh is not None:
+                self._add_extra_sh(extra_sh)
+
+    def _add_extra_sh(self, extra_sh):
+        t = extra_sh.detach().clone() if self.is_cuda else extra_sh.detach().clone()
+        if self._world() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        if self.average:
+            t.div_(self._world())
+        self.sh_sum = self.sh_sum + t.view(self.sh_sum.shape)
 
     def wait(self):
         if self.is_cuda and self._done is not None:

@@ -54,7 +54,7 @@ def _lib():
         lib.gsr_tracker_set_frame.argtypes = [vp, vp, vp]
         lib.gsr_tracker_set_pose.argtypes = [vp, fp, fp]
         lib.gsr_tracker_run.argtypes = [vp, ctypes.POINTER(TrackParams), ci, fp,
-                                        ctypes.POINTER(TrackResult)]
+                                        ctypes.POINTER(TrackResult), vp]
         lib.gsr_last_error.restype = ctypes.c_char_p
         _LIB = lib
     return _LIB
@@ -99,6 +99,7 @@ class PoseTracker:
         self.M = int(num_sh_coeffs)
         self.max_iterations = int(max_iterations)
         self._keep = {}
+        self._device = torch.device("cuda", torch.cuda.current_device())
 
     def close(self):
         if getattr(self, "_h", None):
@@ -110,6 +111,7 @@ class PoseTracker:
     def set_scene(self, means3D, opacities, shs=None, colors_precomp=None, scales=None,
                   rotations=None, cov3D_precomp=None, bg=None, scale_modifier=1.0):
         P = self.P
+        self._device = means3D.device
         self._keep["scene"] = (means3D, opacities, shs, colors_precomp, scales, rotations,
                                cov3D_precomp, bg)
         _check(_lib().gsr_tracker_set_scene(
@@ -139,7 +141,11 @@ class PoseTracker:
                          prm["lr_rot"], prm["lr_trans"], prm["beta1"], prm["beta2"], prm["eps"])
         hist = (ctypes.c_float * int(iterations))()
         res = TrackResult()
-        _check(_lib().gsr_tracker_run(self._h, ctypes.byref(cp), int(iterations), hist, ctypes.byref(res)))
+        # the tracker's private stream is ordered after the CURRENT torch stream: the scene / frame
+        # tensors are usually the result of asynchronous torch work queued there (gsr_b200.h)
+        cur = torch.cuda.current_stream(self._device).cuda_stream
+        _check(_lib().gsr_tracker_run(self._h, ctypes.byref(cp), int(iterations), hist, ctypes.byref(res),
+                                      ctypes.c_void_p(cur)))
         return dict(q=list(res.q), t=list(res.t), loss=list(hist), last_dL_dview=list(res.last_dL_dview),
                     last_grad=list(res.last_grad), last_twist_grad=list(res.last_twist_grad),
                     num_rendered=res.num_rendered, retries=res.retries,

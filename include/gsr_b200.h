@@ -29,6 +29,10 @@
  *    aligned to at least 256 bytes that stays valid until the matching backward has run
  *    (the reference uses std::function<char*(size_t)> resize lambdas for the same purpose,
  *    rasterize_points.cu:27-33).  Their internal layout is private to this library;
+ *  - rotations, dL_dconic, dL_drot (and shs / dL_dsh for the bulk-copy path, which otherwise falls
+ *    back) are accessed with 128-bit loads / stores and must be 16-byte aligned; a misaligned pointer
+ *    is rejected with GSR_E_INVALID (fresh torch allocations always are aligned; the torch shim
+ *    re-packs offset views);
  *  - outputs need not be pre-zeroed: every output element is written by the call;
  *  - every entry point returns 0 on success and a negative GSR_E_* code on failure;
  *    gsr_last_error() gives a thread-local human-readable message.
@@ -43,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GSR_B200_ABI_VERSION 3
+#define GSR_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define GSR_API __attribute__((visibility("default")))
@@ -67,7 +71,13 @@ GSR_API const char* gsr_last_error(void);
 /* Number of floats of caller-provided, uninitialised device scratch a backward call needs. */
 GSR_API size_t gsr_backward_scratch_floats(int P);
 
-/* Tuning switches (process-wide, not part of the reference surface).
+/* Tuning switches (not part of the reference surface).  gsr_set_option changes the PROCESS-WIDE
+ * DEFAULT; every entry point copies the defaults into a thread-local snapshot when it starts and
+ * uses only that copy, so a call never sees a switch change half way through and concurrent calls
+ * from several threads / streams / devices do not share mutable option state.  None of the switches
+ * changes a result beyond the order of floating-point additions.  All other per-call state of the
+ * library (the speculative-binning size estimate, pinned read-back slots, kernel attributes) is kept
+ * per (device, image size, Gaussian count) context, see "async_binning".
  *   "exact_ng"      1: gsr_full_forward returns the exact number of valid (pixel, Gaussian) pairs
  *                   like the reference (costs a second host sync per forward); 0 (default): skip
  *                   the count and the sync and return 0 — the reference's Python only hands the
@@ -88,16 +98,17 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   duplicate count (+25 %) and enqueues the scatter and the per-tile sort before
  *                   the host has read this frame's count, so the GPU does not idle during the
  *                   read-back (guarded kernels; the binning is redone when the estimate was too
- *                   small); 0: wait for the count first, exact buffer size.
+ *                   small); 0: wait for the count first, exact buffer size.  The estimate is kept per
+ *                   (device, width, height, P) context, so rasterizers of different shapes in one
+ *                   process (640x480 tracking + 1080p mapping, one thread per GPU) do not disturb each
+ *                   other; after a miss a context speculates again only once a frame's counts would
+ *                   have fitted the previous frame's estimate.
  *   "bulk_sh"       1 (default): the per-Gaussian kernels move SH rows (M = 16 or 4, 16-byte aligned)
  *                   between global and shared memory with cp.async.bulk (TMA), one row per thread and
  *                   only for Gaussians that survive culling; 0: block-wide coalesced staging.
  *   "cnt_stride"    spacing (in 32-bit words, 1..32, default 8 = one per 32-byte sector) of the per-tile
  *                   entry counters / scatter cursors: neighbouring tiles' atomics no longer serialise on
  *                   one cache line (measured: preprocess_fwd 0.078 -> 0.069 ms, scatter 0.059 -> 0.042 ms).
- *   "bwd_prefetch"  0 (default): the packed backward blend kernel gathers a round's records in front of the
- *                   round; 1: it prefetches the next round's records with cp.async underneath the current
- *                   round (same results; written from the ncu stall profile, not yet timed on a GPU).
  *   "track_headroom_pct" head room (percent, default 50) of the tracker's binning buffer over the
  *                   counts of its probing forward; negative values force the overflow / retry path
  *                   (test hook).
@@ -114,6 +125,9 @@ GSR_API int gsr_get_option(const char* key);
  * GSR_STAGE_COUNT entries; any may be NULL. */
 #define GSR_STAGE_COUNT 10
 GSR_API int gsr_stage_times(double* ms, long long* scopes, long long* launches, int reset);
+/* Kernels (and memset nodes) this library has launched in this process since the last reset, counted
+ * on the host at launch time, independent of "stage_timing" (CUB calls count as one). */
+GSR_API long long gsr_launch_count(int reset);
 GSR_API const char* gsr_stage_name(int stage);
 
 /* Optional extras of the backward calls (not part of the reference surface; pass NULL for none).
@@ -241,9 +255,11 @@ GSR_API int gsr_sh_grad_from_view_ptrs(int P, int D, int M, const float* means3D
 /* In-switch (NVLS) all-reduce of this rank's 1/world slice of count_floats floats starting
  * offset_floats into a symmetric buffer, given the buffer's MULTICAST alias: multimem.ld_reduce sums
  * the replicas in the NVSwitch, multimem.st writes the sums back to every replica.  All ranks call it
- * (between two barriers of their own) and the whole range is all-reduced.  offset / count: multiples of 4. */
+ * (between two barriers of their own) and the whole range is all-reduced.  offset / count: multiples of 4.
+ * max_blocks > 0 confines the kernel to that many CTAs (the reduction is a chain of switch round trips,
+ * not bandwidth bound, so a few CTAs are enough and the rest of the GPU stays free for a concurrent kernel). */
 GSR_API int gsr_nvls_allreduce_slice(float* multicast_ptr, size_t offset_floats, size_t count_floats,
-                                     int rank, int world, void* stream);
+                                     int rank, int world, int max_blocks, void* stream);
 
 /* ---- pose tracker (not part of the reference surface) ------------
  * K iterations of CG-SLAM's tracking loop — render(-light, map_off) -> masked L1 colour + depth loss
@@ -298,9 +314,16 @@ GSR_API int gsr_tracker_set_frame(gsr_tracker* t, const float* gt_color, const f
 /* Host pointers; resets the Adam state. */
 GSR_API int gsr_tracker_set_pose(gsr_tracker* t, const float* quat_wxyz, const float* trans);
 /* Runs `iterations` tracking iterations from the current pose (Adam state carries over between
- * calls) and blocks until they are done.  loss_history (host, [iterations]) and result may be NULL. */
+ * calls) and blocks until they are done.  loss_history (host, [iterations]) and result may be NULL.
+ * Stream contract: the tracker works on a private non-blocking stream.  Before it reads the borrowed
+ * scene / frame tensors it waits (on the device) for everything enqueued so far on `caller_stream`
+ * (a cudaStream_t as void*; NULL = the legacy default stream) — the stream on which the caller
+ * produced or updated those tensors (activations, optimiser steps, the in-place copy of a new frame).
+ * Because the call blocks until the iterations are done, work enqueued afterwards on any stream
+ * sees the tracker's reads completed.  Tensors written by OTHER streams must be ordered into
+ * caller_stream by the caller. */
 GSR_API int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iterations,
-                            float* loss_history, gsr_track_result* result);
+                            float* loss_history, gsr_track_result* result, void* caller_stream);
 
 /* replaces Rasterizer::markVisible (rasterizer.h:24-29): present[i] = view-space z > 0.2.
  * `present` is one byte per Gaussian (0/1). */

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(built.core_library_path())
     for s in declared_symbols():
         assert hasattr(lib, s), "libgsr_b200.so does not export %s" % s
-    assert lib.gsr_abi_version() == 3
+    assert lib.gsr_abi_version() == 4
 
 
 def test_scratch_size_and_options(built):
@@ -43,6 +43,35 @@ def test_scratch_size_and_options(built):
     lib.gsr_set_option(b"exact_ng", 0)
     assert lib.gsr_set_option(b"no_such_option", 1) == -1
     assert b"unknown option" in lib.gsr_last_error()
+
+
+def test_options_are_snapshotted_per_call_and_launch_counter_exists(built):
+    """gsr_set_option changes the process-wide default only; gsr_launch_count counts on the host."""
+    lib = ctypes.CDLL(built.core_library_path())
+    lib.gsr_launch_count.restype = ctypes.c_longlong
+    assert lib.gsr_launch_count(1) >= 0 and lib.gsr_launch_count(0) == 0
+    old = lib.gsr_set_option(b"cnt_stride", 4)
+    assert lib.gsr_get_option(b"cnt_stride") == 4
+    lib.gsr_set_option(b"cnt_stride", old)
+    assert lib.gsr_get_option(b"bwd_prefetch") == -1   # removed in round 2 (measured slower)
+
+
+def test_misaligned_128bit_operands_are_rejected_without_a_gpu(built):
+    """rotations / dL_dconic / dL_drot are accessed with 128-bit loads and stores: a pointer that is
+    not 16-byte aligned is refused with GSR_E_INVALID instead of faulting on the device."""
+    lib = ctypes.CDLL(built.core_library_path())
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    ok, bad = ctypes.c_void_p(4096), ctypes.c_void_p(4096 + 4)
+    cf, nr = ctypes.c_float, ctypes.c_int(0)
+    alloc = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)(lambda c, n: None)
+    rc = lib.gsr_light_forward(alloc, None, alloc, None, alloc, None, 4, 0, 0, ok, 16, 16, ok, None, ok, ok, ok,
+                               cf(1.0), bad, None, ok, ok, ok, cf(1.0), cf(1.0), 0, ok, ok, ok, ok, ok, ok,
+                               ok, ok, ok, 0, None, ctypes.byref(nr))
+    assert rc == -1 and b"16-byte aligned" in lib.gsr_last_error()
+    rc = lib.gsr_full_backward(4, 0, 0, 0, ok, 16, 16, ok, None, ok, ok, cf(1.0), ok, None, ok, ok, ok, cf(1.0),
+                               cf(1.0), ok, ok, ok, ok, ok, ok, ok, ok, bad, ok, ok, ok, ok, ok, ok, ok, ok, ok, ok,
+                               ok, ok, None, None)
+    assert rc == -1 and b"16-byte aligned" in lib.gsr_last_error()
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu(built):
@@ -62,16 +91,16 @@ def test_extension_entry_points_validate_arguments_without_a_gpu(built):
     lib.gsr_tracker_create.restype = ctypes.c_void_p
     assert lib.gsr_tracker_create(0, 3, 16, 64, 48, ctypes.c_float(1.0), ctypes.c_float(1.0), None, 8) is None
     assert b"bad arguments" in lib.gsr_last_error()
-    assert lib.gsr_tracker_run(None, None, 1, None, None) == -1
+    assert lib.gsr_tracker_run(None, None, 1, None, None, None) == -1
     assert lib.gsr_tracker_set_scene(None, None, None, None, None, None, ctypes.c_float(1.0), None, None, None) == -1
     assert lib.gsr_tracker_set_frame(None, None, None) == -1
     assert lib.gsr_tracker_set_pose(None, None, None) == -1
     lib.gsr_tracker_destroy(None)  # no-op
     # offset not a multiple of 4 floats / NULL multicast pointer / rank out of range
     f = ctypes.c_void_p(256)
-    assert lib.gsr_nvls_allreduce_slice(None, ctypes.c_size_t(0), ctypes.c_size_t(16), 0, 2, None) == -1
-    assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(2), ctypes.c_size_t(16), 0, 2, None) == -1
-    assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(0), ctypes.c_size_t(16), 2, 2, None) == -1
+    assert lib.gsr_nvls_allreduce_slice(None, ctypes.c_size_t(0), ctypes.c_size_t(16), 0, 2, 0, None) == -1
+    assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(2), ctypes.c_size_t(16), 0, 2, 0, None) == -1
+    assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(0), ctypes.c_size_t(16), 2, 2, 0, None) == -1
     assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, None, 1, None, None, None, None) == -1
     assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, f, 17, f, f, f, None) == -1   # more than 16 views
     assert lib.gsr_sh_grad_from_view_ptrs(0, 3, 16, None, 0, None, None, None, None) == 0

@@ -447,33 +447,88 @@ def test_packed_and_scalar_backward_kernels_agree(built, variant):
 
 
 def test_speculative_binning_overflow_is_redone(built):
-    """async_binning sizes the binning buffer from the previous frame: a small frame followed by a
-    much larger one (and by one with much longer tile lists) must redo the binning and stay exact."""
+    """async_binning sizes the binning buffer from the previous frame of the same (device, W, H, P)
+    context: a frame of small splats followed by one with many more duplicates (and much longer tile
+    lists) must redo the binning and stay exact; after a miss the context does not speculate until a
+    frame's counts would have fitted the previous estimate."""
     sc = ge.load_scene_module()
     mod = built.load_variant("light")
-    cam_s = sc.make_camera(64, 48)
-    small = sc.make_scene(300, cam_s, (1.0, 3.0), seed=46)
-    cam_b = sc.make_camera(320, 240)
-    big = sc.make_scene(30000, cam_b, (2.0, 14.0), seed=47)
-    cot_s, cot_b = sc.make_cotangents(cam_s, 3), sc.make_cotangents(cam_b, 3)
+    cam = sc.make_camera(320, 240)
+    small = sc.make_scene(30000, cam, (0.3, 0.6), seed=46)
+    big = sc.make_scene(30000, cam, (2.0, 14.0), seed=47)
+    cot = sc.make_cotangents(cam, 3)
     pu.set_option("async_binning", 0)
     try:
-        ref_o, ref_g = pu.run_variant(mod, "light", cam_b, big, cot_b)
+        ref_o, ref_g = pu.run_variant(mod, "light", cam, big, cot)
     finally:
         pu.set_option("async_binning", 1)
-    for _ in range(2):
-        pu.run_variant(mod, "light", cam_s, small, cot_s)      # leaves a tiny estimate behind
-        o, g = pu.run_variant(mod, "light", cam_b, big, cot_b)  # overflows it
+
+    def check(o, g=None):
         for k in ref_o:
             if k != "gau_uncertainty":
                 assert np.array_equal(o[k], ref_o[k]), k
-        for k in ref_g:
+        for k in (ref_g if g is not None else {}):
             rel, _ = pu.grad_mismatch(g[k], ref_g[k], rtol=1e-4)
             assert rel < 1e-4, k
-    o, g = pu.run_variant(mod, "light", cam_b, big, cot_b)      # estimate now fits: speculative path
-    for k in ref_o:
-        if k != "gau_uncertainty":
-            assert np.array_equal(o[k], ref_o[k]), k
+    for _ in range(2):
+        pu.run_variant(mod, "light", cam, small, cot)      # leaves a small estimate behind ...
+        pu.run_variant(mod, "light", cam, small, cot)      # ... and marks the context stable
+        check(*pu.run_variant(mod, "light", cam, big, cot))  # speculates, overflows, is redone
+    for _ in range(3):                                     # estimate fits again: the speculative path
+        check(*pu.run_variant(mod, "light", cam, big, cot))
+
+
+def test_two_rasterizers_interleaved_on_two_streams(built):
+    """Library state is per (device, image size, Gaussian count) context: a 640x480 -light tracker-size
+    rasterizer and a 1080p-ish -full one, interleaved frame by frame on two streams of one process, give
+    the same results as when each runs alone (the speculation estimates do not disturb each other)."""
+    sc = ge.load_scene_module()
+    cam_a, cam_b = sc.make_camera(320, 240), sc.make_camera(480, 272)
+    scene_a = sc.make_scene(20000, cam_a, (1.0, 8.0), seed=71)
+    scene_b = sc.make_scene(60000, cam_b, (1.0, 10.0), seed=72, backdrop=True)
+    cot_a, cot_b = sc.make_cotangents(cam_a, 3), sc.make_cotangents(cam_b, 2)
+    light, full = built.load_variant("light"), built.load_variant("full")
+    ref_a = pu.run_variant(light, "light", cam_a, scene_a, cot_a)
+    ref_b = pu.run_variant(full, "full", cam_b, scene_b, cot_b)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            got_a = pu.run_variant(light, "light", cam_a, scene_a, cot_a)
+        with torch.cuda.stream(s2):
+            got_b = pu.run_variant(full, "full", cam_b, scene_b, cot_b)
+        for (ro, rg), (go, gg) in ((ref_a, got_a), (ref_b, got_b)):
+            for k in ro:
+                if k != "gau_uncertainty":
+                    assert np.array_equal(go[k], ro[k]), k
+            for k in rg:
+                rel, _ = pu.grad_mismatch(gg[k], rg[k], rtol=1e-4)
+                assert rel < 1e-4, k
+
+
+def test_offset_views_are_accepted(built):
+    """Contiguous views at a storage offset that is not a multiple of 16 bytes (rotations / SH sliced out
+    of a larger buffer) work through the torch shim, like with the reference."""
+    sc, cam, scene = _scene(1500, 160, 96, seed=81)
+    cot = sc.make_cotangents(cam, 3)
+    mod = built.load_variant("light")
+    ref_o, ref_g = pu.run_variant(mod, "light", cam, scene, cot)
+    P = scene.means3D.shape[0]
+    big_r = torch.zeros(P * 4 + 1)
+    big_r[1:] = scene.rotations.reshape(-1)
+    big_s = torch.zeros(P * 48 + 1)
+    big_s[1:] = scene.shs.reshape(-1)
+    d = lambda t: t.to(DEV)
+    rot = d(big_r)[1:].view(P, 4).requires_grad_(True)
+    shs = d(big_s)[1:].view(P, 16, 3).requires_grad_(True)
+    assert rot.data_ptr() % 16 != 0 and shs.data_ptr() % 16 != 0
+    means = d(scene.means3D).requires_grad_(True)
+    rs = pu.settings_for(mod, "light", cam, scene, DEV)
+    res = mod.GaussianRasterizer(rs)(means3D=means, means2D=torch.zeros_like(means, requires_grad=True),
+                                     opacities=d(scene.opacities), shs=shs, scales=d(scene.scales), rotations=rot,
+                                     viewmatrix=d(cam.viewmatrix), gt_depth=d(scene.gt_depth))
+    (res[0] * d(cot[0])).sum().backward()
+    assert np.array_equal(res[0].detach().cpu().numpy(), ref_o["color"])
+    assert rot.grad is not None and shs.grad is not None and torch.isfinite(rot.grad).all()
 
 
 def test_very_long_tile_list_falls_back_to_radix(built):
@@ -742,6 +797,47 @@ def test_factorized_sh_exchange_matches_summed_sh_gradients(built, variant):
         torch.cuda.synchronize()
         rel, _ = pu.grad_mismatch(v["shs"].cpu().numpy(), plain[-1]["shs"], rtol=1e-3)
         assert rel < 1e-4
+    finally:
+        red.detach()
+
+
+@pytest.mark.parametrize("mode", ["allreduce", "factorized_sh"])
+def test_two_backwards_per_exchange_add_up(built, mode):
+    """The gradient arena is one-shot: with two views per rank (two backwards before the exchange) the
+    first backward writes the arena, the second returns fresh tensors that autograd accumulates — the
+    exchanged gradients are the SUM of both views, not the last one."""
+    variant = "full"
+    sc, cam0, scene = _scene(2000, 160, 96, seed=63)
+    mod = built.load_variant(variant)
+    dp = ge.load_dp_module()
+    cams = [sc.make_camera(160, 96, seed=k) for k in range(2)]
+    cot = sc.make_cotangents(cam0, 2)
+    plain = [pu.run_variant(mod, variant, c, scene, cot)[1] for c in cams]
+    want = {k: plain[0][k].astype(np.float64) + plain[1][k].astype(np.float64)
+            for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    d = lambda t, rg=False: t.to(DEV).clone().requires_grad_(rg)
+    params = dict(means3D=d(scene.means3D, True), shs=d(scene.shs, True), opacities=d(scene.opacities, True),
+                  scales=d(scene.scales, True), rotations=d(scene.rotations, True))
+    shapes = {k: tuple(v.shape) for k, v in params.items()}
+    red = dp.SceneGradReducer(shapes, DEV, mode=mode, means3D=params["means3D"], sh_degree=3)
+    assert red.attach(mod)
+    try:
+        for step in range(2):            # second step: the arena has been re-armed by reduce_async
+            for t in params.values():
+                t.grad = None
+            for c in cams:
+                rs = pu.settings_for(mod, variant, c, scene, DEV)
+                res = mod.GaussianRasterizer(rs)(
+                    means3D=params["means3D"], means2D=torch.zeros_like(params["means3D"], requires_grad=True),
+                    opacities=params["opacities"], shs=params["shs"], scales=params["scales"],
+                    rotations=params["rotations"], viewmatrix=d(c.viewmatrix), gt_depth=d(scene.gt_depth))
+                ((res[0] * d(cot[0])).sum() + (res[2] * d(cot[1][0])).sum() + (res[3] * d(cot[1][1])).sum()).backward()
+            red.reduce_async({k: v.grad for k, v in params.items()})
+            got = red.wait()
+            torch.cuda.synchronize()
+            for k in want:
+                rel, _ = pu.grad_mismatch(got[k].detach().cpu().numpy().reshape(want[k].shape), want[k], rtol=1e-4)
+                assert rel < 1e-4, (step, k, rel)
     finally:
         red.detach()
 

@@ -189,3 +189,24 @@ def test_bad_arguments_are_rejected(built):
     with pytest.raises(ValueError):
         trk.set_frame(s["gt_color"].cpu(), s["gt_depth"])
     trk.close()
+
+
+def test_tracker_waits_for_the_callers_stream(built):
+    """The tracker works on a private stream; gsr_tracker_run orders it after the caller's current
+    stream, so a frame copied into the borrowed tensors by still-running asynchronous torch work is
+    the frame the tracker sees."""
+    s = _setup()
+    trk = _tracker(s, max_iterations=8)
+    want = trk.run(3)                                   # tracked against the true frame
+    frame_c, frame_d = s["gt_color"].clone(), s["gt_depth"].clone()
+    side = torch.cuda.Stream()
+    s["gt_color"].zero_()
+    s["gt_depth"].fill_(1.0)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(200_000_000)                  # ~0.1 s of pending work in front of the copy
+        s["gt_color"].copy_(frame_c)
+        s["gt_depth"].copy_(frame_d)
+        trk.set_pose(s["q0"], s["t0"])
+        got = trk.run(3)                                # must see the copied frame, not the zeros
+    assert _rel(got["loss"], want["loss"]) < 1e-5 and _rel(got["q"], want["q"]) < 1e-6
