@@ -353,8 +353,13 @@ def parity_report(ge, mod, variant, cam, scene, cot, device, oracle_result, alig
         if drop_view:
             g_a.pop("viewmatrix", None), g_b.pop("viewmatrix", None)
         st = {}
-        ok, lines = pu.compare_runs(o_m, g_a, o_r, g_b, flip_budget=1e-3, grad_budget=1e-2, strict=strict, stats=st)
+        ok, lines = pu.compare_runs(o_m, g_a, o_r, g_b, flip_budget=1e-3, grad_budget=1e-2, strict=strict, stats=st,
+                                    outliers_ok=not strict)
         st["ok"] = bool(ok)
+        st["criterion"] = ("strict: 0 image elements over 1e-4, integers equal, every gradient within 1e-3 of its "
+                           "tensor's maximum") if strict else (
+            "fp32 CPU port, not bit-identical to either CUDA build: <= 1e-3 of the image elements over 1e-4 "
+            "(flipped hard decisions), <= 1e-2 of the gradient elements outside 1e-3")
         if not ok:
             st["report"] = [l for l in lines if "FAIL" in l]
         return st

@@ -120,6 +120,7 @@ struct FwdArgs {
   const float* viewmatrix; const float* projmatrix; const float* cam_pos;
   float tan_fovx, tan_fovy; int prefiltered;
   const float* gt_depth; int* radii; int debug; cudaStream_t stream;
+  float* gau_unc; int* gau_px;   // -light: per-Gaussian statistics, zeroed by preprocess_fwd (NULL for -full)
 };
 
 int check_common(const char* who, int P, int width, int height, const float* means3D,
@@ -196,15 +197,19 @@ int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinS
 
   const bool tile_local = options().tile_sort != 0;
   {
-    StageScope st(ST_MEMSET, a.stream, 2);
-    GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
+    // the only zero-fill of the forward: the per-tile entry counters preprocess_fwd adds to.  (The
+    // counter block is initialised by scan_tiles_kernel, -light's per-Gaussian statistics by
+    // preprocess_fwd itself; the radix path still clears the counter block here.)
+    StageScope st(ST_MEMSET, a.stream, 1);
     if (tile_local)
       GSR_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles * cnt_stride(), a.stream));
+    else
+      GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
   }
   int rc = launch_preprocess_fwd(a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations,
                                  a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, cam,
                                  a.radii, g, tile_local ? img.tile_count : nullptr,
-                                 a.prefiltered != 0, a.debug != 0, a.stream);
+                                 a.prefiltered != 0, a.debug != 0, a.stream, a.gau_unc, a.gau_px);
   if (rc != GSR_OK) return rc;
   return run_binning(a.P, cam, a.radii, g, a.binning_alloc, a.binning_ctx, b, img, num_rendered,
                      a.debug != 0, a.stream);
@@ -323,15 +328,10 @@ int gsr_light_forward(
   FwdArgs a{geom_alloc, geom_ctx, binning_alloc, binning_ctx, img_alloc, img_ctx, P, D, M,
             background, width, height, means3D, shs, colors_precomp, opacities, scales,
             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx,
-            tan_fovy, prefiltered, gt_depth, radii, debug, s};
+            tan_fovy, prefiltered, gt_depth, radii, debug, s, gau_uncertainty, gau_related_pixels};
   Camera cam; GeomState g; BinState b; ImgState img;
   rc = forward_front(a, kLight, cam, g, b, img, num_rendered);
   if (rc != GSR_OK) return rc;
-  {
-    StageScope st(ST_MEMSET, s, 2);
-    GSR_CUDA_OK(cudaMemsetAsync(gau_uncertainty, 0, (size_t)P * sizeof(float), s));
-    GSR_CUDA_OK(cudaMemsetAsync(gau_related_pixels, 0, (size_t)P * sizeof(int), s));
-  }
   return launch_render_fwd_light(cam, g, b, img, background, gt_depth, out_color, out_depth,
                                  out_median_depth, out_alpha, out_depth_var, gau_uncertainty,
                                  gau_related_pixels, debug != 0, s);
@@ -370,7 +370,7 @@ int gsr_full_forward(
   FwdArgs a{geom_alloc, geom_ctx, binning_alloc, binning_ctx, img_alloc, img_ctx, P, D, M,
             background, width, height, means3D, shs, colors_precomp, opacities, scales,
             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx,
-            tan_fovy, prefiltered, gt_depth, radii, 0, s};
+            tan_fovy, prefiltered, gt_depth, radii, 0, s, nullptr, nullptr};
   Camera cam; GeomState g; BinState b; ImgState img;
   rc = forward_front(a, kFull, cam, g, b, img, num_rendered);
   if (rc != GSR_OK) return rc;
@@ -420,11 +420,14 @@ int gsr_light_backward(
   if (rc != GSR_OK) return rc;
   rc = rederive(kLight, P, R, width, height, geom_buffer, binning_buffer, img_buffer, g, b, img, cam);
   if (rc != GSR_OK) return rc;
+  // scratch: acc [16 P] | last-block counter (one 64-byte line) | pose partials; one memset clears
+  // the accumulator lines and the counter
   float* acc = scratch;
-  float* partials = scratch + (size_t)P * kAccStride;
+  unsigned int* done_counter = reinterpret_cast<unsigned int*>(scratch + (size_t)P * kAccStride);
+  float* partials = scratch + (size_t)P * kAccStride + 16;
   {
     StageScope st(ST_MEMSET, s);
-    GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
+    GSR_CUDA_OK(cudaMemsetAsync(acc, 0, ((size_t)P * kAccStride + 16) * sizeof(float), s));
   }
   const bool want_gauss = !map_off, want_pose = !track_off;
   if (want_gauss || want_pose) {
@@ -446,7 +449,7 @@ int gsr_light_backward(
   }
   return launch_preprocess_bwd(kLight, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
-                               out, want_gauss, want_pose, debug != 0, s);
+                               out, want_gauss, want_pose, debug != 0, s, done_counter);
 }
 
 int gsr_full_backward(
@@ -480,11 +483,14 @@ int gsr_full_backward(
   if (rc != GSR_OK) return rc;
   rc = rederive(kFull, P, R, width, height, geom_buffer, binning_buffer, img_buffer, g, b, img, cam);
   if (rc != GSR_OK) return rc;
+  // scratch: acc [16 P] | last-block counter (one 64-byte line) | pose partials; one memset clears
+  // the accumulator lines and the counter
   float* acc = scratch;
-  float* partials = scratch + (size_t)P * kAccStride;
+  unsigned int* done_counter = reinterpret_cast<unsigned int*>(scratch + (size_t)P * kAccStride);
+  float* partials = scratch + (size_t)P * kAccStride + 16;
   {
     StageScope st(ST_MEMSET, s);
-    GSR_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * kAccStride * sizeof(float), s));
+    GSR_CUDA_OK(cudaMemsetAsync(acc, 0, ((size_t)P * kAccStride + 16) * sizeof(float), s));
   }
   BlendGrads cot{dL_dpix, dL_dpix_depth, nullptr, dL_dpix_uncertainty};
   rc = launch_render_bwd(kFull, cam, g, b, img, background, gt_depth, nullptr, cot, acc, P, R, false, false, s);
@@ -502,7 +508,7 @@ int gsr_full_backward(
   }
   return launch_preprocess_bwd(kFull, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
-                               out, true, true, false, s);
+                               out, true, true, false, s, done_counter);
 }
 
 }  // extern "C"

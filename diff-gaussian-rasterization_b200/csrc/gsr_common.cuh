@@ -483,7 +483,8 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
                           const float* shs, const float* cov3D_precomp,
                           const float* colors_precomp, const Camera& cam, int* radii,
                           GeomState& g, uint32_t* tile_count /* zeroed, or NULL */, bool prefiltered,
-                          bool debug, cudaStream_t stream);
+                          bool debug, cudaStream_t stream, float* zero_f32 = nullptr /* [P] or NULL */,
+                          int* zero_i32 = nullptr /* [P] or NULL */);
 
 int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_alloc_fn alloc,
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
@@ -549,7 +550,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
                           const float* cov3D_precomp, const Camera& cam, const float* perspec,
                           const GeomState& g, const float* acc, float* pose_partials,
                           const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
-                          cudaStream_t stream);
+                          cudaStream_t stream, unsigned int* done_counter /* zeroed, or NULL */);
 
 int preprocess_bwd_blocks(int P);
 int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float* means3D,

@@ -18,6 +18,7 @@ namespace gsr {
 namespace {
 
 constexpr int kBwdThreads = 128;
+constexpr int kFuseFinalizeMaxBlocks = 8192;  // fused last-block pose reduction up to this many blocks
 
 __device__ __forceinline__ float3 ld3(const float* p, int idx) {
   return make_float3(p[3 * idx], p[3 * idx + 1], p[3 * idx + 2]);
@@ -54,7 +55,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ perspec, float fx, float fy, float tanx, float tany,
                       const float* __restrict__ acc, const float4* __restrict__ g_rec, int img_w,
                       int img_h, float* __restrict__ pose_partials, GaussGradOut out,
-                      bool want_gauss, bool want_pose, float* __restrict__ acc_clear) {
+                      bool want_gauss, bool want_pose, float* __restrict__ acc_clear,
+                      unsigned int* __restrict__ done_counter) {
   extern __shared__ __align__(16) float sh_smem[];  // [kBwdThreads][row] SH in, dL/dSH out
   __shared__ float s_pose[kBwdThreads / 32][12];
   __shared__ uint64_t s_bar;
@@ -496,6 +498,51 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       pose_partials[(size_t)blockIdx.x * 12 + threadIdx.x] = s;
     }
   }
+  // Fused final reduction (done_counter != NULL): the LAST block to finish adds all blocks' partials
+  // in a fixed order (deterministic, no float atomics) and writes the 16-float dL/dviewmatrix — the
+  // separate pose_finalize launch disappears.  Entries 3, 7, 11, 15 are 0, as in the reference.
+  if (done_counter != nullptr) {
+    __shared__ bool s_last;
+    __shared__ float s_fin[kBwdThreads / 32][12];
+    if (!want_pose) {
+      if (blockIdx.x == 0 && threadIdx.x < 16) out.dL_dview[threadIdx.x] = 0.f;
+    } else {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        float a[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k] = 0.f;
+        const float4* p4 = reinterpret_cast<const float4*>(pose_partials);
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kBwdThreads) {
+          const float4 q0 = __ldcg(p4 + 3 * (size_t)b), q1 = __ldcg(p4 + 3 * (size_t)b + 1), q2 = __ldcg(p4 + 3 * (size_t)b + 2);
+          a[0] += q0.x; a[1] += q0.y; a[2] += q0.z; a[3] += q0.w;
+          a[4] += q1.x; a[5] += q1.y; a[6] += q1.z; a[7] += q1.w;
+          a[8] += q2.x; a[9] += q2.y; a[10] += q2.z; a[11] += q2.w;
+        }
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          float s = a[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) s_fin[warp][k] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+          float t = 0.f;
+#pragma unroll
+          for (int wq = 0; wq < kBwdThreads / 32; ++wq) t += s_fin[wq][threadIdx.x];
+          const int col = threadIdx.x / 3, rowi = threadIdx.x % 3;  // pose[] order: (v0,v1,v2),(v4,v5,v6),...
+          out.dL_dview[4 * col + rowi] = t;
+          if (rowi == 0) out.dL_dview[4 * col + 3] = 0.f;
+        }
+      }
+    }
+  }
   if (TMA && sh_out && idx < P) bulk_s2g_wait_read();
 }
 
@@ -535,8 +582,10 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
                           const float* cov3D_precomp, const Camera& cam, const float* perspec,
                           const GeomState& g, const float* acc, float* pose_partials,
                           const GaussGradOut& out, bool want_gauss, bool want_pose, bool debug,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, unsigned int* done_counter) {
   const int blocks = (P + kBwdThreads - 1) / kBwdThreads;
+  // one block adds `blocks` x 48 bytes of partials: worth a launch up to ~1 M Gaussians
+  if (blocks > kFuseFinalizeMaxBlocks) done_counter = nullptr;
   const bool tma = shs != nullptr && (M == 16 || M == 4) && options().bulk_sh != 0 &&
                    (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
                    (out.dL_dsh == nullptr || (reinterpret_cast<uintptr_t>(out.dL_dsh) & 15) == 0);
@@ -544,7 +593,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
                       : tma          ? sizeof(float) * kBwdThreads * (size_t)bulk_row_floats(M * 3)
                                      : sizeof(float) * kBwdThreads * (size_t)(M * 3 + 1);
   const float* cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
-  StageScope st(ST_PRE_BWD, stream, 2);
+  StageScope st(ST_PRE_BWD, stream, done_counter != nullptr ? 1 : 2);
   // With want_gauss == false (-light, map_off: light backward.cu:593,609,654,666;
   // rasterizer_impl.cu:467) the kernel itself writes the zero gradients: no memset passes.
   if (shs == nullptr && out.dL_dsh != nullptr && M > 0) {
@@ -557,7 +606,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1><<<blocks, kBwdThreads, smem, stream>>>( \
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
-      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr)
+      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr, done_counter)
 #define GSR_PRE_BWD_M(V)                                                                         \
   if (tma) {                                                                                     \
     if (M == 16) { GSR_PRE_BWD(V, 16, true); } else { GSR_PRE_BWD(V, 4, true); }                 \
@@ -579,8 +628,10 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
 #undef GSR_PRE_BWD
     GSR_LAUNCH_OK(debug, stream);
   }
-  pose_finalize_kernel<<<12, 1024, 0, stream>>>(blocks, pose_partials, out.dL_dview, want_pose);
-  GSR_LAUNCH_OK(debug, stream);
+  if (done_counter == nullptr) {
+    pose_finalize_kernel<<<12, 1024, 0, stream>>>(blocks, pose_partials, out.dL_dview, want_pose);
+    GSR_LAUNCH_OK(debug, stream);
+  }
   return GSR_OK;
 }
 
@@ -599,7 +650,7 @@ int launch_preprocess_bwd_partials(int variant, int P, int D, int M, const float
   preprocess_bwd_kernel<kLight, 0, false><<<blocks, kBwdThreads, 0, stream>>>(
       P, D, M, means3D, radii, nullptr, g.clamped, nullptr, nullptr, 1.0f, g.cov3D, cam.view, cam.proj,
       cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc, g.rec, cam.W,
-      cam.H, pose_partials, GaussGradOut{}, false, true, clear_acc ? acc : nullptr);
+      cam.H, pose_partials, GaussGradOut{}, false, true, clear_acc ? acc : nullptr, nullptr);
   GSR_LAUNCH_OK(false, stream);
   return GSR_OK;
 }

@@ -189,7 +189,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int* __restrict__ radii, float4* __restrict__ rec, float* __restrict__ cov3Ds,
                       unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                       uint2* __restrict__ rects, uint32_t* __restrict__ tile_count,
-                      bool prefiltered, bool tight_tiles, uint32_t cs) {
+                      bool prefiltered, bool tight_tiles, uint32_t cs,
+                      float* __restrict__ zero_f32, int* __restrict__ zero_i32) {
   // TMA == false: [kPreThreads][M*3+1] slab staged with coalesced loads by the whole block.
   // TMA == true : [kPreThreads][bulk_row_floats(M*3)] rows, each fetched by its own thread with one
   //               cp.async.bulk AFTER the cull tests (culled Gaussians cost no SH traffic) and
@@ -320,6 +321,10 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     radii[idx] = my_radius_i;
     tiles_touched[idx] = my_tiles;
     rects[idx] = my_rect;
+    // -light: the forward blend accumulates per-Gaussian statistics with atomics; clearing them here
+    // replaces two memset passes
+    if (zero_f32 != nullptr) zero_f32[idx] = 0.0f;
+    if (zero_i32 != nullptr) zero_i32[idx] = 0;
   }
 
   // every thread waits: the block's shared memory must outlive the copies in flight
@@ -357,7 +362,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
                           const float* shs, const float* cov3D_precomp,
                           const float* colors_precomp, const Camera& cam, int* radii,
                           GeomState& g, uint32_t* tile_count, bool prefiltered, bool debug,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, float* zero_f32, int* zero_i32) {
   if (colors_precomp == nullptr && (shs == nullptr || M <= 0 || M > kMaxCoeffs)) {
     set_error("SH colours need 1 <= M <= %d coefficients (got %d)", kMaxCoeffs, M);
     return GSR_E_INVALID;
@@ -383,7 +388,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,  \
       cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,        \
       g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0,            \
-      (uint32_t)cnt_stride())
+      (uint32_t)cnt_stride(), zero_f32, zero_i32)
   if (tma) {
     if (M == 16) { GSR_PRE_FWD(16, true); } else { GSR_PRE_FWD(4, true); }
   } else {

@@ -90,8 +90,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                     rs.perspec_matrix, rs.track_off, rs.map_off)
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_view) = _guarded(
             _C.rasterize_gaussians_backward, bwd_args, rs.debug, "snapshot_bw.dump", "backward")
-        with torch.no_grad():
-            g_view = torch.sum(g_view, dim=0)  # [1,4,4] here ([H*W,4,4] upstream) -> [4,4]
+        # [1,4,4] here, already summed over pixels on the device ([H*W,4,4] + torch.sum upstream,
+        # L/__init__.py:160): a view is enough, no reduction kernel
+        g_view = g_view[0] if g_view.shape[0] == 1 else torch.sum(g_view, dim=0)
         return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, g_view,
                 None, None)
 

@@ -139,7 +139,7 @@ def grad_mismatch(a, b, rtol=GRAD_RTOL):
 
 
 def compare_runs(outs_a, grads_a, outs_b, grads_b, flip_budget=2e-4, grad_budget=2e-3,
-                 label_a="ours", label_b="ref", strict=False, stats=None):
+                 label_a="ours", label_b="ref", strict=False, stats=None, outliers_ok=False):
     """Compare two (outputs, grads) pairs; returns (ok, report lines).
 
     strict=True is the north star's gate, used against the reference build (golden vectors and live
@@ -147,6 +147,9 @@ def compare_runs(outs_a, grads_a, outs_b, grads_b, flip_budget=2e-4, grad_budget
     1e-3 of the tensor's largest magnitude.  strict=False (CUDA vs the CPU oracle, whose expf / FMA
     contraction differ in the last bit) keeps small budgets for flipped hard decisions (alpha < 15/255,
     T < 1e-4, median crossing); the gradient bar is the same 1e-3.
+    outliers_ok=True (bench.py's oracle leg at 1 M Gaussians) judges gradients by the SHARE of
+    elements outside 1e-3 only: between two fp32 implementations a handful of hard decisions flip at
+    that size, and one flipped pixel moves its Gaussians' gradients by more than 1e-3 of the maximum.
     `stats`, when given, receives the violation counts (bench.py's "parity" object)."""
     ok = True
     lines = []
@@ -176,7 +179,7 @@ def compare_runs(outs_a, grads_a, outs_b, grads_b, flip_budget=2e-4, grad_budget
         if a is None or b is None:
             continue
         g, fb = grad_mismatch(a, b)
-        good = g <= GRAD_RTOL and (fb <= grad_budget or k == "viewmatrix")
+        good = (g <= GRAD_RTOL or outliers_ok) and (fb <= grad_budget or k == "viewmatrix")
         st["grad_max_rel"] = max(st["grad_max_rel"], g)
         st["grad_frac_bad_max"] = max(st["grad_frac_bad_max"], fb)
         lines.append("grad %-15s global_rel %.3e frac_bad %.3e %s" % (k, g, fb, "" if good else "FAIL"))

@@ -773,6 +773,7 @@ def test_factorized_sh_exchange_matches_summed_sh_gradients(built, variant):
     try:
         rows = []
         for c, ref in zip(cams, plain):
+            mod._C.arm_grad_arena()                        # the arena is one-shot: one view per exchange
             _, got = pu.run_variant(mod, variant, c, scene, cot)
             torch.cuda.synchronize()
             assert got["shs"] is None                      # dL_dsh is not materialised per view

@@ -4,9 +4,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity_util as pu
 ge = pu.ge
+for kv in os.environ.get("GSR_TEST_OPTS", "").split(","):
+    if kv:
+        k, v = kv.split("=")
+        pu.set_option(k, int(v))
+SIZES = ((3000, 200, 120), (20000, 330, 250)) if not os.environ.get("GSR_SANITIZE_SMALL") else ((1500, 120, 72),)
 sc = ge.load_scene_module()
 for variant in ("light", "full"):
-    for (P, W, H) in ((3000, 200, 120), (20000, 330, 250)):
+    for (P, W, H) in SIZES:
         cam = sc.make_camera(W, H)
         scene = sc.make_scene(P, cam, (1.0, 10.0), seed=7)
         cot = sc.make_cotangents(cam, 3 if variant == "light" else 2)
