@@ -52,6 +52,7 @@ struct Options {
   int track_headroom_pct;
   int bulk_sh;
   int cnt_stride;
+  int bwd_occ;
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the

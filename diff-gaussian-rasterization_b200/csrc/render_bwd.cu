@@ -554,6 +554,290 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   }
 }
 
+
+// =================================================================================================
+// Quarter-list variant of the packed kernel (default): same pixel arithmetic (two vertically adjacent
+// pixels per lane, fp32x2), but every QUARTER warp — 8 lanes = a 4x4 pixel block — walks its OWN
+// compacted entry list, the four quarters side by side.  An 8x8 block is hit by 3.2 M (block, entry)
+// pairs per C3 frame with only 31 % of its 64 pixel slots blended; its four 4x4 blocks have 55 % of
+// their slots blended, and walking their lists in lock step needs 2.3 M full-cost iterations instead
+// of 3.2 M (C4: 4.0 M instead of 7.0 M; tools/blend_stats.py).  The shared-memory reduction then
+// produces four 8-lane sums per slot (one per quarter / Gaussian) instead of one 32-lane sum:
+// 13 x 4 (slot, quarter) sums are spread over the 32 lanes in two passes of 2 x LDS.128 each, and
+// each pass ends in one red.add instruction whose lanes address up to four accumulator lines.
+// Further per-iteration savings against render_bwd2_kernel: exp(power) is ex2.approx(power * log2 e)
+// (the backward's tolerance is 1e-3; the forward keeps expf and decides what is blended through
+// n_contrib), list positions come from one subtraction, the first-contributor select is one
+// compare-and-select per pixel.
+// =================================================================================================
+constexpr int kBwdQThreads = 128;
+constexpr int kBwdQWarps = kBwdQThreads / 32;
+constexpr int kBwdQBatch = 128;  // entries staged per round (one per thread)
+
+__device__ __forceinline__ float fast_exp(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+// Opaque copy: the value stays in a register; without it the compiler rebuilds per-thread shared
+// addresses from threadIdx inside the hot loop (5-8 instructions each time it needs one).
+__device__ __forceinline__ unsigned pin_reg(unsigned v) {
+  unsigned r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// sum of 8 consecutive floats in shared memory (2 x LDS.128)
+__device__ __forceinline__ float row8_sum(unsigned addr) {
+  f2 a0, a1, b0, b1;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(addr + 16) : "memory");
+  const f2 t = f2_add(f2_add(a0, a1), f2_add(b0, b1));
+  return f2_lo(t) + f2_hi(t);
+}
+
+template <int VARIANT, bool POSE_ONLY, int MINB>
+__global__ void __launch_bounds__(kBwdQThreads, MINB)
+render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
+                   const float4* __restrict__ rec, const float* __restrict__ bg,
+                   const float* __restrict__ gt_depth,
+                   const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
+                   const float* __restrict__ final_Ts,    // full
+                   const uint32_t* __restrict__ n_contrib,
+                   const uint32_t* __restrict__ first_contrib,  // full
+                   const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepths,
+                   const float* __restrict__ dL_dmedians,  // light
+                   const float* __restrict__ dL_dvars,     // light: depth_var, full: uncertainty
+                   float* __restrict__ acc) {
+  // staged entry, duplicated into pairs: q0 = (xg, pc | yg, yg)  q1 = (A, A | -B, -B)
+  //   q2 = (C, C | o, o)  q3 = (depth, depth | r, r)  q4 = (g, g | b, b)
+  __shared__ ulonglong2 s_q[5][kBwdQBatch];
+  __shared__ int s_id[kBwdQBatch];
+  __shared__ unsigned short s_mask[kBwdQBatch];
+  // per-warp entry lists of the four quarters, interleaved: byte [k][q] = k-th entry of quarter q, so
+  // that ONE broadcast LDS.32 per iteration fetches the four quarters' entries
+  __shared__ __align__(16) unsigned char s_list[kBwdQWarps][kBwdQBatch][4];
+  __shared__ __align__(16) float s_red[kRedVals][red_row(kBwdQWarps)];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int quarter = lane >> 3, ql = lane & 7;
+  // lists start zeroed: slots beyond a quarter's length are read (and ignored) by its lanes
+  reinterpret_cast<uint4*>(&s_list[0][0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
+  // warp -> 8x8 block (column warp & 1, row warp >> 1); quarter -> 4x4 block inside it; lane -> a 1x2 column
+  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (quarter & 1) * 4 + (ql & 3);
+  const int py0 = blockIdx.y * kTileY + (warp >> 1) * 8 + (quarter >> 1) * 4 + 2 * (ql >> 2);
+  const int py1 = py0 + 1;
+  const bool in_a = px < W && py0 < H, in_b = px < W && py1 < H;
+  const uint32_t pix_a = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
+  const uint32_t pix_b = pix_a + (uint32_t)W;
+  const float pxf = (float)px;
+  const f2 npy2 = f2_pack(-(float)py0, -(float)py1);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
+  // bit of this warp's quarter 0 in block_mask16 (bit = 4 * block row + block column of the 4x4 blocks);
+  // quarters 1, 2, 3 are bits +1, +4, +5
+  const int sub0 = 4 * (2 * (warp >> 1)) + 2 * (warp & 1);
+
+  const uint2 range = ranges[tile];
+  const int walk = (int)tile_last[tile];  // entries [0, walk) were used by some pixel
+  const int rounds = (walk + kBwdQBatch - 1) / kBwdQBatch;
+  const size_t HW = (size_t)H * (size_t)W;
+
+  float Tf_a = 0.f, Tf_b = 0.f, g0a = 0.f, g0b = 0.f, g1a = 0.f, g1b = 0.f, g2a = 0.f, g2b = 0.f;
+  float gda = 0.f, gdb = 0.f, gva = 0.f, gvb = 0.f, gta = 0.f, gtb = 0.f, gma = 0.f, gmb = 0.f;
+  int lc_a = 0, lc_b = 0, fm1_a = -1, fm1_b = -1;   // fm1: 0-based position of the front-most contributor
+  if (in_a) {
+    Tf_a = (VARIANT == kLight) ? (1 - alphas[pix_a]) : final_Ts[pix_a];
+    lc_a = (int)n_contrib[pix_a];
+    g0a = dL_dpix[pix_a]; g1a = dL_dpix[HW + pix_a]; g2a = dL_dpix[2 * HW + pix_a];
+    gda = dL_ddepths[pix_a]; gva = dL_dvars != nullptr ? dL_dvars[pix_a] : 0.f; gta = gt_depth[pix_a];
+    if (VARIANT == kLight && dL_dmedians != nullptr) gma = dL_dmedians[pix_a];
+    if (VARIANT == kFull) fm1_a = (int)first_contrib[pix_a] - 1;
+  }
+  if (in_b) {
+    Tf_b = (VARIANT == kLight) ? (1 - alphas[pix_b]) : final_Ts[pix_b];
+    lc_b = (int)n_contrib[pix_b];
+    g0b = dL_dpix[pix_b]; g1b = dL_dpix[HW + pix_b]; g2b = dL_dpix[2 * HW + pix_b];
+    gdb = dL_ddepths[pix_b]; gvb = dL_dvars != nullptr ? dL_dvars[pix_b] : 0.f; gtb = gt_depth[pix_b];
+    if (VARIANT == kLight && dL_dmedians != nullptr) gmb = dL_dmedians[pix_b];
+    if (VARIANT == kFull) fm1_b = (int)first_contrib[pix_b] - 1;
+  }
+  const f2 dLp0 = f2_pack(g0a, g0b), dLp1 = f2_pack(g1a, g1b), dLp2 = f2_pack(g2a, g2b);
+  const f2 dLd = f2_pack(gda, gdb), dLv = f2_pack(gva, gvb), dLv_x2 = f2_pack(2.f * gva, 2.f * gvb);
+  const f2 ngt2 = f2_pack(-gta, -gtb);
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  // -T_final * (bg . dL/dpixel): the background term of dL/dalpha is this times 1 / (1 - alpha)
+  const f2 tfbg2 = f2_pack(-Tf_a * (bg0 * g0a + bg1 * g1a + bg2 * g2a), -Tf_b * (bg0 * g0b + bg1 * g1b + bg2 * g2b));
+  const f2 one2 = f2_pack(1.f, 1.f), mone2 = f2_pack(-1.f, -1.f), mhalf2 = f2_pack(-0.5f, -0.5f);
+  f2 T2 = f2_pack(Tf_a, Tf_b);
+  f2 Bc0 = 0ull, Bc1 = 0ull, Bc2 = 0ull, Bd = 0ull, Bv = 0ull;  // colour / depth / var "behind" the entry
+  bool mid_a = true, mid_b = true;
+  using RS = RedSet<VARIANT, POSE_ONLY>;
+  constexpr unsigned kRowBytes = red_row(kBwdQWarps) * 4;
+  const unsigned red_st = pin_reg(smem_u32(&s_red[0][tid]));
+  // reducing lane: slot (lane & 7) [+ 8 in the second pass] of its OWN quarter: conflict-free (row stride
+  // 16 bytes mod 128), and the lane already holds that quarter's entry index
+  const unsigned red_ld = pin_reg(smem_u32(&s_red[ql][(tid & ~31) + quarter * 8]));
+  const unsigned list_w = pin_reg(smem_u32(&s_list[warp][0][0]));
+  const unsigned qshift = pin_reg((unsigned)quarter * 8u);
+  const unsigned ql4 = (unsigned)ql * 4u;            // byte offset of this lane's slot in an accumulator line
+
+  for (int i = 0; i < rounds; ++i) {
+    __syncthreads();
+    const int progress = i * kBwdQBatch + tid;
+    unsigned my_mask = 0u;
+    if (progress < walk) {
+      const int id = (int)point_list[range.x + (walk - progress - 1)];
+      const float4* r = rec + 3 * (size_t)id;
+      const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+      s_id[tid] = id;
+      my_mask = block_mask16(q0, q1, tile_x0, tile_y0);
+      s_q[0][tid] = make_ulonglong2(f2_pack(q0.x, q1.z), f2_pack(q0.y, q0.y));
+      s_q[1][tid] = make_ulonglong2(f2_pack(q0.z, q0.z), f2_pack(-q0.w, -q0.w));
+      s_q[2][tid] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q1.y));
+      s_q[3][tid] = make_ulonglong2(f2_pack(q1.w, q1.w), f2_pack(q2.x, q2.x));
+      s_q[4][tid] = make_ulonglong2(f2_pack(q2.y, q2.y), f2_pack(q2.z, q2.z));
+    }
+    s_mask[tid] = (unsigned short)my_mask;
+    __syncthreads();
+
+    // per-quarter compaction: entries whose cut ellipse can touch the quarter's 4x4 block
+    const int nb = min(kBwdQBatch, walk - i * kBwdQBatch);
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c = 0; c * 32 < nb; ++c) {
+      const int jj = c * 32 + lane;
+      const unsigned m = (jj < nb) ? ((unsigned)s_mask[jj] >> sub0) : 0u;
+      const unsigned b0 = __ballot_sync(0xffffffffu, m & 1u), b1 = __ballot_sync(0xffffffffu, m & 2u);
+      const unsigned b2 = __ballot_sync(0xffffffffu, m & 16u), b3 = __ballot_sync(0xffffffffu, m & 32u);
+      if (m & 1u) s_list[warp][c0 + __popc(b0 & lt)][0] = (unsigned char)jj;
+      if (m & 2u) s_list[warp][c1 + __popc(b1 & lt)][1] = (unsigned char)jj;
+      if (m & 16u) s_list[warp][c2 + __popc(b2 & lt)][2] = (unsigned char)jj;
+      if (m & 32u) s_list[warp][c3 + __popc(b3 & lt)][3] = (unsigned char)jj;
+      c0 += __popc(b0); c1 += __popc(b1); c2 += __popc(b2); c3 += __popc(b3);
+    }
+    __syncwarp();
+    const int cnt = quarter == 0 ? c0 : (quarter == 1 ? c1 : (quarter == 2 ? c2 : c3));
+    const int cnt_max = max(max(c0, c1), max(c2, c3));
+    const int posbase = walk - i * kBwdQBatch - 1;   // 0-based list position of staged entry j = posbase - j
+
+    for (int k = 0; k < cnt_max; ++k) {
+      const bool active = k < cnt;
+      // one broadcast load: the four quarters' k-th entries; slots past a list's end hold an older
+      // (in-range) index and are masked by `active`
+      const int j = (int)((lds_u32(list_w + 4u * (unsigned)k) >> qshift) & 0xFFu);
+      const int pos = posbase - j;
+      const ulonglong2* eq = &s_q[0][j];
+      const ulonglong2 e0 = eq[0], e1 = eq[kBwdQBatch], e2 = eq[2 * kBwdQBatch];
+      const float dx = GSR_SUB(f2_lo(e0.x), pxf);
+      const float pc = f2_hi(e0.x);
+      const f2 dx2 = f2_pack(dx, dx);
+      const f2 dy2 = f2_add(e0.y, npy2);
+      // pair_power for both pixels, same rounding sequence as the forward
+      const f2 qf = f2_fma(dx2, f2_mul(dx2, e1.x), f2_mul(dy2, f2_mul(dy2, e2.x)));
+      const f2 pw2 = f2_fma(qf, mhalf2, f2_mul(dy2, f2_mul(dx2, e1.y)));
+      const float pw_a = f2_lo(pw2), pw_b = f2_hi(pw2);
+      bool va = active && (pos < lc_a) && !(pw_a > 0.0f) && !(pw_a < pc);
+      bool vb = active && (pos < lc_b) && !(pw_b > 0.0f) && !(pw_b < pc);
+      if (!__any_sync(0xffffffffu, va || vb)) continue;
+      const float o = f2_lo(e2.y);
+      float Ga = fast_exp(pw_a), Gb = fast_exp(pw_b);
+      float al_a = pair_alpha(o, Ga), al_b = pair_alpha(o, Gb);
+      va = va && !(al_a < kAlphaMin);
+      vb = vb && !(al_b < kAlphaMin);
+      const unsigned vmask = __ballot_sync(0xffffffffu, va || vb);
+      if (vmask == 0u) continue;
+      if (!va) { Ga = 0.f; al_a = 0.f; }
+      if (!vb) { Gb = 0.f; al_b = 0.f; }
+      const f2 G2 = f2_pack(Ga, Gb), alpha2 = f2_pack(al_a, al_b);
+
+      const ulonglong2 e3 = eq[3 * kBwdQBatch], e4 = eq[4 * kBwdQBatch];
+      const f2 om2 = f2_fma(alpha2, mone2, one2);  // 1 - alpha (>= 0.01)
+      const f2 inv2 = f2_pack(fast_rcp(f2_lo(om2)), fast_rcp(f2_hi(om2)));
+      T2 = f2_mul(T2, inv2);
+      const f2 aT2 = f2_mul(alpha2, T2);
+      // c - B for colour, depth and var
+      const f2 d0 = f2_fma(Bc0, mone2, e3.y), d1 = f2_fma(Bc1, mone2, e4.x), d2 = f2_fma(Bc2, mone2, e4.y);
+      const f2 dgt2 = f2_add(e3.x, ngt2);
+      const f2 cvar2 = f2_mul(dgt2, dgt2);
+      const f2 dd = f2_fma(Bd, mone2, e3.x), dv = f2_fma(Bv, mone2, cvar2);
+      const f2 colour_part = f2_fma(d2, dLp2, f2_fma(d1, dLp1, f2_mul(d0, dLp0)));
+      const f2 depth_part = f2_mul(dd, dLd);
+      f2 dLa = f2_fma(dv, dLv, f2_add(colour_part, depth_part));
+      // B <- B + alpha (c - B)
+      Bc0 = f2_fma(alpha2, d0, Bc0);
+      Bc1 = f2_fma(alpha2, d1, Bc1);
+      Bc2 = f2_fma(alpha2, d2, Bc2);
+      Bd = f2_fma(alpha2, dd, Bd);
+      Bv = f2_fma(alpha2, dv, Bv);
+      const f2 aTd = f2_mul(aT2, dLd);
+      // dL/dalpha = T * (...) - T_final / (1 - alpha) * (bg . dL/dpixel)
+      dLa = f2_fma(inv2, tfbg2, f2_mul(dLa, T2));
+      const f2 w2 = f2_mul(G2, dLa);
+      const f2 wx = f2_mul(w2, dx2), wy = f2_mul(w2, dy2);
+
+      f2 v[kRedVals];
+      v[ACC_MX] = wx;
+      v[ACC_MY] = wy;
+      v[ACC_CA] = f2_mul(wx, dx2);
+      v[ACC_CB] = f2_mul(wx, dy2);
+      v[ACC_CC] = f2_mul(wy, dy2);
+      v[ACC_OP] = w2;
+      v[ACC_R] = f2_mul(aT2, dLp0);
+      v[ACC_G] = f2_mul(aT2, dLp1);
+      v[ACC_B] = f2_mul(aT2, dLp2);
+      v[ACC_DEPTH] = f2_fma(f2_mul(aT2, dgt2), dLv_x2, aTd);
+      v[ACC_PGX] = 0ull;
+      v[ACC_PGY] = 0ull;
+      v[ACC_PD] = 0ull;
+      v[ACC_MED] = 0ull;
+      if (VARIANT == kLight) {
+        v[ACC_PD] = aTd;
+        // median: the first valid entry met from the back whose restored T exceeds 0.5
+        float med_a = 0.f, med_b = 0.f;
+        if (va && mid_a && f2_lo(T2) > 0.5f) { med_a = gma; mid_a = false; }
+        if (vb && mid_b && f2_hi(T2) > 0.5f) { med_b = gmb; mid_b = false; }
+        v[ACC_MED] = f2_pack(med_a, med_b);
+      } else {
+        // pose terms of the reference's ComputePG: colour through ndc without the background
+        // term (full backward.cu:746-777, :1028-1072); depth only from the front-most valid
+        // contributor of the pixel, because dd_dv* is assigned, not accumulated (:1278-1289).
+        const bool fa = va & (pos == fm1_a), fb = vb & (pos == fm1_b);
+        const f2 fsel = f2_pack(fa ? 1.f : 0.f, fb ? 1.f : 0.f);
+        const f2 pa = f2_mul(T2, f2_fma(fsel, depth_part, colour_part));
+        v[ACC_PD] = f2_mul(fsel, aTd);
+        const f2 q = f2_mul(pa, G2);
+        v[ACC_PGX] = f2_mul(q, dx2);
+        v[ACC_PGY] = f2_mul(q, dy2);
+      }
+      // reduction through shared memory: every lane stores its column (both pixels added first), then
+      // lane (quarter, l) adds the 8 values of its own quarter for slot l (second pass: slot 8 + l) and
+      // issues the red into the quarter's Gaussian
+#pragma unroll
+      for (int qn = 0; qn < RS::N; ++qn)
+        sts_f32(red_st + qn * kRowBytes, f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]));
+      __syncwarp();
+      if ((vmask >> qshift) & 0xFFu) {
+        char* line = reinterpret_cast<char*>(acc + (size_t)s_id[j] * kAccStride);
+        if (POSE_ONLY) {
+          if (ql4 < 4u * RS::N) atomicAdd(reinterpret_cast<float*>(line) + RS::slot((int)(ql4 >> 2)), row8_sum(red_ld));
+        } else {
+          float* dst = reinterpret_cast<float*>(line + ql4);   // slot ql, second pass slot ql + 8
+          if (RS::N >= 8 || ql4 < 4u * RS::N) atomicAdd(dst, row8_sum(red_ld));
+          if (RS::N > 8 && ql4 < 4u * (RS::N - 8)) atomicAdd(dst + 8, row8_sum(red_ld + 8 * kRowBytes));
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 }  // namespace
 
 int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
@@ -562,16 +846,28 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
                       int num_entries, bool pose_only, bool debug, cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_BWD, stream);
-  // auto (2): the packed kernel works on 8x8 pixel blocks and wins when splats are large enough to
-  // fill them (measured: C3, 1.97 duplicates per Gaussian: 0.87 vs 0.96 ms); small splats (C4, 1.30
-  // duplicates per Gaussian: 2.00 vs 1.88 ms) are better served by the 8x4-block kernel.
+  // "bwd_packed": 0 scalar 8x4 kernel, 1 packed 8x8 kernel (one list per warp), 3 packed kernel with
+  // quarter-warp lists, 2 (default) = 3.  "bwd_occ": CTAs per SM the quarter kernel is compiled for
+  // (8 = 64 registers, 7 = 72 registers).
   const int mode = options().bwd_packed;
-  const bool packed = mode == 1 || (mode == 2 && (double)num_entries >= 1.6 * (double)num_gaussians);
+  const bool quarter = mode == 3 || mode == 2;
+  const bool packed = mode == 1;
+  const bool occ7 = options().bwd_occ == 7;
+  (void)num_gaussians; (void)num_entries;
 #define GSR_BWD_ARGS(FT, FC)                                                                       \
   img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas, FT,    \
       img.n_contrib, FC, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar, acc
+#define GSR_BWDQ(V, PO, FT, FC)                                                                    \
+  do {                                                                                             \
+    if (occ7) render_bwdq_kernel<V, PO, 7><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC)); \
+    else render_bwdq_kernel<V, PO, 8><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC));    \
+  } while (0)
   if (variant == kLight) {
-    if (packed && pose_only)
+    if (quarter && pose_only)
+      GSR_BWDQ(kLight, true, nullptr, nullptr);
+    else if (quarter)
+      GSR_BWDQ(kLight, false, nullptr, nullptr);
+    else if (packed && pose_only)
       render_bwd2_kernel<kLight, true><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
     else if (packed)
       render_bwd2_kernel<kLight, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
@@ -580,11 +876,14 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
     else
       render_bwd_kernel<kLight, false><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
   } else {
-    if (packed)
+    if (quarter)
+      GSR_BWDQ(kFull, false, img.final_T, img.first_contrib);
+    else if (packed)
       render_bwd2_kernel<kFull, false><<<grid, kBwd2Threads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
     else
       render_bwd_kernel<kFull, false><<<grid, kTileThreads, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
   }
+#undef GSR_BWDQ
 #undef GSR_BWD_ARGS
   GSR_LAUNCH_OK(debug, stream);
   return GSR_OK;
