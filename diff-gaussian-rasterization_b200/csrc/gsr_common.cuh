@@ -130,7 +130,7 @@ struct GeomState {
   float4* rec;             // [3P] packed blend record:
                            //   rec[3i+0] = (x_pix, y_pix, conic.a, conic.b)
                            //   rec[3i+1] = (conic.c, opacity, power_cut, depth)
-                           //   rec[3i+2] = (r, g, b, 0)
+                           //   rec[3i+2] = (r, g, b, power_sure)
   float* cov3D;            // [6P] (only when computed from scale/rotation)
   unsigned char* clamped;  // [P] bit k set <=> colour channel k clamped at 0
   uint32_t* tiles_touched; // [P]

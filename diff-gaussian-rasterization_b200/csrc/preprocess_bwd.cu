@@ -18,7 +18,10 @@ namespace gsr {
 namespace {
 
 constexpr int kBwdThreads = 128;
-constexpr int kFuseFinalizeMaxBlocks = 8192;  // fused last-block pose reduction up to this many blocks
+// The fused last-block pose reduction reads blocks x 48 bytes with ONE block: measured 34 us at 7813 blocks
+// (C3) against ~5 us for the 12-CTA finalize kernel, so it is used for small scenes only (C2: 782 blocks),
+// where the saved launch matters and the tail is ~1 us.
+constexpr int kFuseFinalizeMaxBlocks = 1024;
 
 __device__ __forceinline__ float3 ld3(const float* p, int idx) {
   return make_float3(p[3 * idx], p[3 * idx + 1], p[3 * idx + 2]);
@@ -143,6 +146,19 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     const float g_pd = a3.x, g_med = a3.y;
 
     const float3 m = ld3(means3D, idx);
+    // the remaining inputs are requested here as well, in front of the arithmetic: the gradient stores
+    // below may alias them as far as the compiler knows, so it cannot hoist these loads itself, and each
+    // one left in place is another exposed round trip in a latency-bound kernel
+    float3 in_sc = make_float3(0.f, 0.f, 0.f);
+    float4 in_q = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned char in_cb = 0;
+    if (want_gauss) {
+      if (scales != nullptr) {
+        in_sc = ld3(scales, idx);
+        in_q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+      }
+      if (shs != nullptr) in_cb = clamped[idx];
+    }
     const float4 m_hom = xform_point_4x4(m, proj);
     const float m_w = 1.0f / (m_hom.w + 0.0000001f);
     float3 dq = make_float3(0.f, 0.f, 0.f);  // dRGB.dL/dcolor contracted with d(rgb)/d(campos)
@@ -256,7 +272,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         const float3 dir_orig = make_float3(m.x - campos.x, m.y - campos.y, m.z - campos.z);
         const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
         const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-        const unsigned char cb = clamped[idx];
+        const unsigned char cb = in_cb;
         const float dR[3] = {g_r * ((cb & 1) ? 0.f : 1.f), g_g * ((cb & 2) ? 0.f : 1.f),
                              g_b * ((cb & 4) ? 0.f : 1.f)};
         st3(out.dL_dcolor_masked, idx, dR[0], dR[1], dR[2]);
@@ -375,8 +391,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 
       // ---------------- scale / rotation backward ----------------
       if (scales != nullptr) {
-        const float3 sc = ld3(scales, idx);
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+        const float3 sc = in_sc;
+        const float4 q = in_q;
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         M3 R;
         R.c[0][0] = 1.f - 2.f * (y * y + z * z); R.c[0][1] = 2.f * (x * y - r * z); R.c[0][2] = 2.f * (x * z + r * y);

@@ -178,7 +178,7 @@ constexpr int kMaxCoeffs = 16;
 // streams its slab with coalesced 128-bit loads into shared memory (row stride M*3+1 floats to
 // spread banks) and each thread then reads its own row.
 template <int MT, bool TMA>  // MT: compile-time number of SH coefficients (16 / 9 / 4 / 1) or 0 = runtime M
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, 7)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ scales, float scale_modifier,
                       const float* __restrict__ rotations, const float* __restrict__ opacities,
@@ -193,8 +193,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       float* __restrict__ zero_f32, int* __restrict__ zero_i32) {
   // TMA == false: [kPreThreads][M*3+1] slab staged with coalesced loads by the whole block.
   // TMA == true : [kPreThreads][bulk_row_floats(M*3)] rows, each fetched by its own thread with one
-  //               cp.async.bulk AFTER the cull tests (culled Gaussians cost no SH traffic) and
-  //               awaited only where the colour is evaluated.
+  //               cp.async.bulk issued before any arithmetic and awaited only where the colour is
+  //               evaluated.
   extern __shared__ __align__(16) float sh_smem[];
   __shared__ uint64_t s_bar;
   const int base = blockIdx.x * kPreThreads;
@@ -223,11 +223,36 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   float3 p_orig = make_float3(0.f, 0.f, 0.f);
   float2 pix = make_float2(0.f, 0.f);
   float3 conic = make_float3(0.f, 0.f, 0.f);
-  float opacity = 0.f, power_cut = 0.f, depth = 0.f;
+  float opacity = 0.f, power_cut = 0.f, power_sure = 0.f, depth = 0.f;
   uint2 rmin = make_uint2(0u, 0u), rmax = make_uint2(0u, 0u);
 
-  if (idx < P) do {
+  // Every global input of this Gaussian is requested up front — position, scale, rotation, opacity
+  // and (TMA) the SH row — so that the loads are in flight together instead of one dependent round
+  // trip after the other (position -> cull -> scale / rotation -> opacity -> SH row): the kernel is
+  // latency bound (ncu: long-scoreboard stalls 4.8 warps per issue at 40 % occupancy).  Culled
+  // Gaussians (3 % at C3) now cost their 28 + 12 M bytes, which is cheaper than the serialisation.
+  float3 in_scale = make_float3(0.f, 0.f, 0.f);
+  float4 in_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+  float in_opacity = 0.f;
+  if (idx < P) {
     p_orig = ld3(means3D, idx);
+    if (cov3D_precomp == nullptr) {
+      in_scale = ld3(scales, idx);
+      in_rot = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+    }
+    in_opacity = opacities[idx];
+  }
+  if (TMA) {
+    if (idx < P && sh_path) {
+      mbar_arrive_expect_tx(&s_bar, (unsigned)(MT * 3 * sizeof(float)));
+      bulk_g2s(sh_smem + threadIdx.x * kBulkRow, shs + (size_t)idx * (MT * 3),
+               (unsigned)(MT * 3 * sizeof(float)), &s_bar);
+    } else {
+      mbar_arrive(&s_bar);
+    }
+  }
+
+  if (idx < P) do {
     const float3 p_view = xform_point_4x3(p_orig, view);
     if (p_view.z <= 0.2f) {  // near cull (auxiliary.h:154); lateral cull is disabled upstream
       if (prefiltered) {
@@ -246,9 +271,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     if (cov3D_precomp != nullptr) {
       cov3D = cov3D_precomp + (size_t)idx * 6;
     } else {
-      const float3 s = ld3(scales, idx);
-      const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
-      cov3d_from_scale_rot(s, scale_modifier, q, cov_local);
+      cov3d_from_scale_rot(in_scale, scale_modifier, in_rot, cov_local);
 #pragma unroll
       for (int k = 0; k < 6; ++k) cov3Ds[(size_t)idx * 6 + k] = cov_local[k];
       cov3D = cov_local;
@@ -272,24 +295,17 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     live = true;
   } while (false);
 
-  // the SH row of a surviving Gaussian starts its way to shared memory now; everything up to the
-  // colour evaluation overlaps the copy
-  if (TMA) {
-    if (live && sh_path) {
-      mbar_arrive_expect_tx(&s_bar, (unsigned)(MT * 3 * sizeof(float)));
-      bulk_g2s(sh_smem + threadIdx.x * kBulkRow, shs + (size_t)idx * (MT * 3),
-               (unsigned)(MT * 3 * sizeof(float)), &s_bar);
-    } else {
-      mbar_arrive(&s_bar);
-    }
-  }
-
   if (live) {
-    opacity = opacities[idx];
+    opacity = in_opacity;
     // power_cut: pairs with power < power_cut cannot reach alpha >= 15/255 (opacity*exp(power)
     // is monotone in power); the 1e-3 margin (0.1 % in alpha) is four orders of magnitude above
     // the rounding error of the exact test that still runs for everything above the cut.
     power_cut = (opacity > 0.0f) ? (logf(kAlphaMin / opacity) - 1e-3f) : 1.0f;
+    // power_sure: pairs with power >= power_sure reach alpha >= 15/255 whatever the last bits of exp()
+    // are (margin 1e-5 >> the rounding of logf / expf / the product, < 1e-6).  The backward, which
+    // evaluates exp with ex2.approx, takes the forward's decision from this bound and re-evaluates the
+    // exact expf only for the rare pairs inside [power_cut, power_sure).
+    power_sure = (opacity > 0.0f) ? (logf(kAlphaMin / opacity) + 1e-5f) : 1.0f;
     if (tight_tiles) {
       // shrink the reference's 3-sigma rectangle to the tiles the alpha >= 15/255 ellipse can reach:
       // tile t holds pixel centres [16t, 16t+15]
@@ -341,7 +357,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     } else {
       rgb = ld3(colors_precomp, idx);
     }
-    rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+    rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, power_sure);
   }
   if (idx < P) clamped[idx] = cbits;
 }

@@ -615,7 +615,7 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
                    const float* __restrict__ dL_dvars,     // light: depth_var, full: uncertainty
                    float* __restrict__ acc) {
   // staged entry, duplicated into pairs: q0 = (xg, pc | yg, yg)  q1 = (A, A | -B, -B)
-  //   q2 = (C, C | o, o)  q3 = (depth, depth | r, r)  q4 = (g, g | b, b)
+  //   q2 = (C, C | o, ps)  q3 = (depth, depth | r, r)  q4 = (g, g | b, b)     (pc / ps = power_cut / power_sure)
   __shared__ ulonglong2 s_q[5][kBwdQBatch];
   __shared__ int s_id[kBwdQBatch];
   __shared__ unsigned short s_mask[kBwdQBatch];
@@ -700,7 +700,7 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       my_mask = block_mask16(q0, q1, tile_x0, tile_y0);
       s_q[0][tid] = make_ulonglong2(f2_pack(q0.x, q1.z), f2_pack(q0.y, q0.y));
       s_q[1][tid] = make_ulonglong2(f2_pack(q0.z, q0.z), f2_pack(-q0.w, -q0.w));
-      s_q[2][tid] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q1.y));
+      s_q[2][tid] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q2.w));
       s_q[3][tid] = make_ulonglong2(f2_pack(q1.w, q1.w), f2_pack(q2.x, q2.x));
       s_q[4][tid] = make_ulonglong2(f2_pack(q2.y, q2.y), f2_pack(q2.z, q2.z));
     }
@@ -746,11 +746,15 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       bool va = active && (pos < lc_a) && !(pw_a > 0.0f) && !(pw_a < pc);
       bool vb = active && (pos < lc_b) && !(pw_b > 0.0f) && !(pw_b < pc);
       if (!__any_sync(0xffffffffu, va || vb)) continue;
-      const float o = f2_lo(e2.y);
+      const float o = f2_lo(e2.y), ps = f2_hi(e2.y);
       float Ga = fast_exp(pw_a), Gb = fast_exp(pw_b);
       float al_a = pair_alpha(o, Ga), al_b = pair_alpha(o, Gb);
-      va = va && !(al_a < kAlphaMin);
-      vb = vb && !(al_b < kAlphaMin);
+      // the forward blended this pair iff min(0.99, o * expf(power)) >= 15/255: certain for power >=
+      // power_sure; the few pairs below it repeat the forward's exact evaluation (divergent, rare)
+      if ((va && pw_a < ps) || (vb && pw_b < ps)) {
+        if (va && pw_a < ps) { Ga = expf(pw_a); al_a = pair_alpha(o, Ga); va = !(al_a < kAlphaMin); }
+        if (vb && pw_b < ps) { Gb = expf(pw_b); al_b = pair_alpha(o, Gb); vb = !(al_b < kAlphaMin); }
+      }
       const unsigned vmask = __ballot_sync(0xffffffffu, va || vb);
       if (vmask == 0u) continue;
       if (!va) { Ga = 0.f; al_a = 0.f; }
@@ -852,7 +856,11 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
   const int mode = options().bwd_packed;
   const bool quarter = mode == 3 || mode == 2;
   const bool packed = mode == 1;
-  const bool occ7 = options().bwd_occ == 7;
+  // measured (C3 / C4, B200): -full 0.590 / 1.19 ms at 7 CTAs per SM vs 0.653 / 1.31 at 8 (the 64-register
+  // build rematerialises shared addresses in the loop); -light is equal at both and a little faster at 8
+  // on small frames.  "bwd_occ" = 7 / 8 forces one, 0 (default) picks per variant.
+  const int occ_opt = options().bwd_occ;
+  const bool occ7 = occ_opt == 7 || (occ_opt != 8 && variant == kFull);
   (void)num_gaussians; (void)num_entries;
 #define GSR_BWD_ARGS(FT, FC)                                                                       \
   img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas, FT,    \

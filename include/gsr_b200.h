@@ -91,9 +91,12 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   segment and each tile is sorted on chip (same order as the reference's
  *                   device-wide (tile | depth) radix sort; tiles with more than 8192 entries make
  *                   the frame fall back to the radix path); 0: always the radix path.
- *   "bwd_packed"    backward blend kernel: 1 = two pixels per lane, packed fp32x2 arithmetic, 8x8
- *                   pixel blocks; 0 = one pixel per lane, 8x4 blocks; 2 (default) = pick per call
- *                   from the number of duplicates per Gaussian (same results up to summation order).
+ *   "bwd_packed"    backward blend kernel: 3 = two pixels per lane, packed fp32x2 arithmetic, every
+ *                   quarter warp (a 4x4 pixel block) walks its own entry list; 1 = the same arithmetic
+ *                   with one list per warp (8x8 block); 0 = one pixel per lane, 8x4 blocks;
+ *                   2 (default) = 3 (same results up to summation order).
+ *   "bwd_occ"       CTAs per SM the quarter-list kernel is built for: 8 (64 registers) or 7 (72
+ *                   registers); 0 (default) = 7 for -full, 8 for -light (measured best).
  *   "async_binning" 1 (default): the forward sizes the binning buffer from the previous frame's
  *                   duplicate count (+25 %) and enqueues the scatter and the per-tile sort before
  *                   the host has read this frame's count, so the GPU does not idle during the
