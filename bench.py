@@ -247,7 +247,7 @@ class Frame:
             ev.record(self.copy_stream)
         return d, ev, slot
 
-    def step_e2e(self):
+    def step_e2e(self, fused_loss=True):
         """One training step with the step's inputs coming from pinned host memory and its result
         (loss, dL/dviewmatrix) going back to the host, organised like an input pipeline: every step
         uploads one step's inputs (the NEXT step's, on a copy stream, while this step computes) and
@@ -262,21 +262,30 @@ class Frame:
         main.wait_event(ev)
         d_view, d_proj, d_campos, d_rgb, d_mm = inp
         view = d_view.detach().requires_grad_(True)   # fresh leaf on the reused storage
-        gt_rgb = d_rgb * (1.0 / 255.0)                # uint8 -> fp32 [3,H,W]
         gt_d = (d_mm * 1e-3).unsqueeze(0)             # int16 millimetres -> fp32 metres [1,H,W]
+        if not (fused_loss and hasattr(self.mod, "rgbd_l1_loss")):
+            gt_rgb = d_rgb * (1.0 / 255.0)            # uint8 -> fp32 [3,H,W]
         rast = self._rasterizer(view.detach(), d_proj, d_campos)
         p = self.params
         res = rast(means3D=p["means3D"], means2D=self.means2D, opacities=p["opacities"], shs=p["shs"],
                    scales=p["scales"], rotations=p["rotations"], viewmatrix=view, gt_depth=gt_d)
         outs = self._outs(res)
         # L1 colour + depth loss (+ median depth and the depth-variance channel for -light, the
-        # silhouette for -full): every differentiable output receives a cotangent, as in `step`
-        loss = (outs[0] - gt_rgb).abs().sum() + (outs[1] - gt_d).abs().sum()
-        if self.variant == "light":
-            loss = loss + (outs[2] - gt_d).abs().sum() + outs[3].sum()
+        # silhouette for -full): every differentiable output receives a cotangent, as in `step`.
+        # The B200 package evaluates it and its cotangents in one pass (its public helper
+        # rgbd_l1_loss, straight from the uint8 / int16 frame); the reference package has no such
+        # helper, its arm (and the "e2e_torch_loss" leg of ours) use the same loss written in torch.
+        helper = getattr(self.mod, "rgbd_l1_loss", None) if fused_loss else None
+        if helper is not None:
+            loss, tensors, cots = helper(res, d_rgb, d_mm)
+            torch.autograd.backward(tensors, cots)
         else:
-            loss = loss + (1.0 - outs[2]).sum()
-        loss.backward()
+            loss = (outs[0] - gt_rgb).abs().sum() + (outs[1] - gt_d).abs().sum()
+            if self.variant == "light":
+                loss = loss + (outs[2] - gt_d).abs().sum() + outs[3].sum()
+            else:
+                loss = loss + (1.0 - outs[2]).sum()
+            loss.backward()
         with torch.no_grad():
             packed = torch.cat([loss.detach().reshape(1), view.grad.reshape(16)])
         slot = self.e2e_steps & 1
@@ -583,9 +592,9 @@ def main():
             reducer.reduce_async(frame.grads())
             reducer.wait()
 
-    def step_e2e():
+    def step_e2e(fused_loss=True):
         frame.zero_grad()
-        frame.step_e2e()
+        frame.step_e2e(fused_loss)
         if reducer is not None:
             reducer.reduce_async(frame.grads())
             reducer.wait()
@@ -648,6 +657,12 @@ def main():
     for _ in range(3):
         step_e2e()
     e2e_ms, e2e_per_step = timed_region(torch, dist, step_e2e, a.steps, world)
+    e2e_torch_ms = None
+    if a.impl == "b200" and hasattr(mod, "rgbd_l1_loss"):
+        # the same end-to-end step with the loss written in torch, exactly as the reference arm runs it
+        for _ in range(2):
+            step_e2e(False)
+        e2e_torch_ms, _ = timed_region(torch, dist, lambda: step_e2e(False), a.steps, world)
     clk = clocks.stop() if rank == 0 else None
 
     if reducer is not None and getattr(reducer, "nvls", None) and rank == 0:
@@ -683,9 +698,16 @@ def main():
                 "d2h_bytes_per_step": frame.d2h_bytes, "ms_per_step": e2e_ms / a.steps,
                 "step_ms": spread(e2e_per_step),
                 "inputs": "camera (3 tensors) + ground-truth RGB-D frame (uint8 colour, int16 mm depth) from "
-                          "pinned host memory; L1 loss in torch on the device; loss + dL/dviewmatrix read back"},
+                          "pinned host memory; L1 loss + cotangents on the device (B200 arm: the package's "
+                          "one-pass rgbd_l1_loss helper; reference arm: the same loss in torch); loss + "
+                          "dL/dviewmatrix read back"},
         "clocks": clk,
     }
+    if e2e_torch_ms is not None:
+        out["e2e_torch_loss"] = {"value": world * 1000.0 / (e2e_torch_ms / a.steps), "unit": UNIT,
+                                 "ms_per_step": e2e_torch_ms / a.steps,
+                                 "note": "the same end-to-end step with the loss evaluated by torch ops, as in "
+                                         "the reference arm"}
     if dp_check is not None:
         out["dp_check"] = dp_check
     if a.impl == "reference":

@@ -17,6 +17,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nvls_allreduce_slice", &nvlsAllreduceSlice, pybind11::arg("multicast_ptr"), pybind11::arg("offset_floats"),
         pybind11::arg("count_floats"), pybind11::arg("rank"), pybind11::arg("world"), pybind11::arg("max_blocks") = 0);
   // extension (not in the reference): in-kernel densification statistics
+  // extension (not in the reference): RGB-D L1 loss + cotangents in one pass over the rendered images
+  m.def("rgbd_l1_loss", &rgbdL1Loss);
   m.def("set_densify_stats", &setDensifyStats, pybind11::arg("grad_accum"), pybind11::arg("denom"),
         pybind11::arg("max_radii2D"));
 }

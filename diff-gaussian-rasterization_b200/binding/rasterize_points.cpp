@@ -499,3 +499,47 @@ torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,
   }
   return present;
 }
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rgbdL1Loss(const torch::Tensor& color, const torch::Tensor& depth, const torch::Tensor& aux0,
+           const torch::Tensor& aux1, const torch::Tensor& gt_color, const torch::Tensor& gt_depth,
+           double w_color, double w_depth, double w_aux0, double w_aux1, double depth_scale,
+           bool depth_mask) {
+  TORCH_CHECK(color.is_cuda() && color.dim() == 3 && color.size(0) == 3, "color must be a [3,H,W] CUDA tensor");
+  const c10::cuda::CUDAGuard guard(color.device());
+  const auto dev = color.device();
+  const int H = color.size(1), W = color.size(2);
+  const int64_t HW = (int64_t)H * W;
+#if defined(GSR_VARIANT_LIGHT)
+  const int variant = 0;
+#else
+  const int variant = 1;
+#endif
+  const auto c = prep(color, dev, "color"), d = prep(depth, dev, "depth"), a0 = prep(aux0, dev, "aux0");
+  const auto a1 = variant == 0 ? prep(aux1, dev, "aux1") : torch::Tensor();
+  TORCH_CHECK(d.defined() && d.numel() == HW && a0.defined() && a0.numel() == HW &&
+                  (variant == 1 || (a1.defined() && a1.numel() == HW)),
+              "depth / aux images must hold H*W values");
+  TORCH_CHECK(gt_color.is_cuda() && gt_color.device() == dev && gt_color.numel() == 3 * HW &&
+                  (gt_color.scalar_type() == torch::kUInt8 || gt_color.scalar_type() == torch::kFloat32),
+              "gt_color must be a uint8 or float32 [3,H,W] tensor on the same device");
+  TORCH_CHECK(gt_depth.is_cuda() && gt_depth.device() == dev && gt_depth.numel() == HW &&
+                  (gt_depth.scalar_type() == torch::kInt16 || gt_depth.scalar_type() == torch::kFloat32),
+              "gt_depth must be an int16 or float32 tensor with H*W values on the same device");
+  const torch::Tensor gc = gt_color.contiguous(), gd = gt_depth.contiguous();
+  auto fopts = color.options().dtype(torch::kFloat32);
+  torch::Tensor loss = torch::empty({1}, fopts);
+  torch::Tensor g_color = torch::empty_like(c), g_depth = torch::empty_like(d), g_a0 = torch::empty_like(a0);
+  torch::Tensor g_a1 = variant == 0 ? torch::empty_like(a1) : torch::Tensor();
+  torch::Tensor scratch = torch::empty({static_cast<long long>(gsr_rgbd_l1_scratch_floats(W, H))}, fopts);
+  gsr_rgbd_l1 prm{(float)w_color, (float)w_depth, (float)w_aux0, (float)w_aux1, 1.0f / 255.0f, (float)depth_scale,
+                  depth_mask ? 1 : 0};
+  const int rc = gsr_rgbd_l1_loss(variant, W, H, fptr(c), fptr(d), fptr(a0), fptr(a1), gc.data_ptr(),
+                                  gc.scalar_type() == torch::kUInt8 ? 1 : 0, gd.data_ptr(),
+                                  gd.scalar_type() == torch::kInt16 ? 1 : 0, &prm, g_color.data_ptr<float>(),
+                                  g_depth.data_ptr<float>(), g_a0.data_ptr<float>(), fptr_mut(g_a1),
+                                  loss.data_ptr<float>(), scratch.data_ptr<float>(),
+                                  at::cuda::getCurrentCUDAStream().stream());
+  check_rc(rc, "gsr_rgbd_l1_loss");
+  return std::make_tuple(loss, g_color, g_depth, g_a0, g_a1);
+}

@@ -100,3 +100,14 @@ torch::Tensor shGradFromViews(const torch::Tensor& means3D, const torch::Tensor&
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,
                           torch::Tensor& projmatrix);
+
+// RGB-D L1 loss and its cotangent images in one pass (gsr_rgbd_l1_loss; not part of the reference
+// surface).  color [3,H,W], depth / aux0 / aux1 [1,H,W] or [H,W] fp32 = the rasterizer's outputs
+// (-light: aux0 = median depth, aux1 = depth_var; -full: aux0 = the opacity map, aux1 ignored);
+// gt_color: uint8 or fp32 [3,H,W]; gt_depth: int16 (scaled by depth_scale) or fp32 [H,W] / [1,H,W].
+// Returns (loss [1], dL_dcolor, dL_ddepth, dL_daux0, dL_daux1) shaped like the inputs.
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rgbdL1Loss(const torch::Tensor& color, const torch::Tensor& depth, const torch::Tensor& aux0,
+           const torch::Tensor& aux1, const torch::Tensor& gt_color, const torch::Tensor& gt_depth,
+           double w_color, double w_depth, double w_aux0, double w_aux1, double depth_scale,
+           bool depth_mask);

@@ -22,7 +22,7 @@ BIND = os.path.join(HERE, "binding")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 CORE_SOURCES = ["api.cu", "preprocess_fwd.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "sh_grad_views.cu",
-                "preprocess_bwd.cu", "tracker.cu"]
+                "preprocess_bwd.cu", "tracker.cu", "loss.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -146,9 +146,10 @@ constexpr int kTileSortThreads = 256;
 // tracker (run_binning_static): ranges are clamped to the buffer and to the longest list the sort
 // was launched for, so that every later kernel stays inside the buffers whatever this frame holds,
 // and counters[3] is raised when something was cut (the host checks it after the fact).
-// Every thread owns kScanPer CONSECUTIVE tiles (one 256-byte run of the spread counters): their loads
-// are issued together, the thread scans them serially, and one warp-shuffle + one shared-memory step
-// scan the 1024 thread totals — 2 barriers per 8192 tiles instead of 4 per 1024.
+// The counters of a chunk of 8192 tiles are read coalesced (thread t reads tiles t, t + 1024, ...: all
+// eight loads in flight), transposed through shared memory so that every thread scans eight CONSECUTIVE
+// tiles serially, one warp-shuffle + one shared-memory step scan the 1024 thread totals, and the range
+// starts go back through shared memory to coalesced stores — 4 barriers per 8192 tiles.
 // reset_counters: this kernel is the first writer of the frame's counter block and initialises all of
 // it (no memset pass); the tracker passes false, its overflow flag is sticky across iterations.
 constexpr int kScanPer = 8;
@@ -156,20 +157,32 @@ __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
                   uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ counters,
                   uint32_t capacity, uint32_t longest_cap, int cs, bool reset_counters) {
+  __shared__ uint32_t s_cnt[1024 * (kScanPer + 1)];   // one pad word per 8: the stride-8 reads become stride 9
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry, s_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto slot = [](int i) { return i + (i >> 3); };
   if (tid == 0) { s_carry = 0; s_max = 0; }
-  __syncthreads();
   uint32_t local_max = 0;
   for (int base = 0; base < tiles; base += 1024 * kScanPer) {
-    const int t0 = base + tid * kScanPer;
-    uint32_t c[kScanPer];
+    uint32_t v[kScanPer];
 #pragma unroll
-    for (int k = 0; k < kScanPer; ++k) c[k] = (t0 + k < tiles) ? tile_count[(size_t)(t0 + k) * cs] : 0u;
+    for (int r = 0; r < kScanPer; ++r) {
+      const int t = base + r * 1024 + tid;
+      v[r] = (t < tiles) ? tile_count[(size_t)t * cs] : 0u;
+    }
+    __syncthreads();   // previous chunk's readers are done with s_cnt; s_carry is visible
+#pragma unroll
+    for (int r = 0; r < kScanPer; ++r) s_cnt[slot(r * 1024 + tid)] = v[r];
+    __syncthreads();
+    uint32_t c[kScanPer];
     uint32_t sum = 0;
 #pragma unroll
-    for (int k = 0; k < kScanPer; ++k) { local_max = max(local_max, c[k]); sum += c[k]; }
+    for (int k = 0; k < kScanPer; ++k) {
+      c[k] = s_cnt[slot(tid * kScanPer + k)];
+      local_max = max(local_max, c[k]);
+      sum += c[k];
+    }
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -191,16 +204,21 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
     const uint32_t carry = s_carry;
     uint32_t start = carry + (warp ? s_warp[warp - 1] : 0u) + incl - sum;
 #pragma unroll
-    for (int k = 0; k < kScanPer; ++k) {
-      if (t0 + k < tiles) {
-        ranges[t0 + k] = make_uint2(min(start, capacity), min(start + min(c[k], longest_cap), capacity));
-        tile_fill[(size_t)(t0 + k) * cs] = start;  // scatter cursor
-      }
+    for (int k = 0; k < kScanPer; ++k) {   // exclusive starts replace the counts in place
+      s_cnt[slot(tid * kScanPer + k)] = start;
       start += c[k];
     }
     __syncthreads();
     if (tid == 1023) s_carry = carry + s_warp[31];
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kScanPer; ++r) {
+      const int t = base + r * 1024 + tid;
+      if (t < tiles) {
+        const uint32_t st = s_cnt[slot(r * 1024 + tid)];
+        ranges[t] = make_uint2(min(st, capacity), min(st + min(v[r], longest_cap), capacity));
+        tile_fill[(size_t)t * cs] = st;  // scatter cursor
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));

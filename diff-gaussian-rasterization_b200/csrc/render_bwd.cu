@@ -856,11 +856,10 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
   const int mode = options().bwd_packed;
   const bool quarter = mode == 3 || mode == 2;
   const bool packed = mode == 1;
-  // measured (C3 / C4, B200): -full 0.590 / 1.19 ms at 7 CTAs per SM vs 0.653 / 1.31 at 8 (the 64-register
-  // build rematerialises shared addresses in the loop); -light is equal at both and a little faster at 8
-  // on small frames.  "bwd_occ" = 7 / 8 forces one, 0 (default) picks per variant.
-  const int occ_opt = options().bwd_occ;
-  const bool occ7 = occ_opt == 7 || (occ_opt != 8 && variant == kFull);
+  // measured (C3 / C4, B200): -full 0.609 / 1.23 ms at 7 CTAs per SM (72 registers) vs 0.667 / 1.33 at 8 (the
+  // 64-register build rematerialises shared addresses in the loop); -light 0.607 vs 0.620 at C3.
+  // "bwd_occ" = 8 forces the 64-register build, anything else the 72-register one.
+  const bool occ7 = options().bwd_occ != 8;
   (void)num_gaussians; (void)num_entries;
 #define GSR_BWD_ARGS(FT, FC)                                                                       \
   img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas, FT,    \

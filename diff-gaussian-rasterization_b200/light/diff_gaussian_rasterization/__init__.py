@@ -18,7 +18,7 @@ import torch.nn as nn
 from . import _C  # noqa: F401  (hard requirement: the CUDA extension)
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
-           "set_densify_stats"]
+           "set_densify_stats", "rgbd_l1_loss"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -105,6 +105,22 @@ def set_densify_stats(grad_accum=None, denom=None, max_radii2D=None):
     e = torch.empty(0)
     _C.set_densify_stats(e if grad_accum is None else grad_accum, e if denom is None else denom,
                          e if max_radii2D is None else max_radii2D)
+
+
+def rgbd_l1_loss(outputs, gt_color, gt_depth, w_color=1.0, w_depth=1.0, w_median=1.0, w_var=1.0,
+                 depth_scale=1e-3, depth_mask=False):
+    """Extension (not in the reference): the RGB-D L1 mapping loss of one frame and the cotangents of
+    the rasterizer's differentiable outputs, in ONE device pass instead of ~30 torch kernels:
+        L = w_color sum|C - C_gt| + w_depth sum_m|D - D_gt| + w_median sum_m|D_med - D_gt| + w_var sum depth_var
+    `outputs` is the tuple GaussianRasterizer returned; gt_color is uint8 (scaled by 1/255) or fp32
+    [3,H,W]; gt_depth int16 (scaled by depth_scale, e.g. millimetres) or fp32 [H,W] / [1,H,W];
+    m = pixels with gt depth > 0 when depth_mask.  Returns (loss [1], tensors, cotangents): run the
+    backward with  torch.autograd.backward(tensors, cotangents)."""
+    color, _radii, depth, median, var = outputs[0], outputs[1], outputs[2], outputs[3], outputs[4]
+    loss, g_c, g_d, g_m, g_v = _C.rgbd_l1_loss(color.detach(), depth.detach(), median.detach(), var.detach(),
+                                               gt_color, gt_depth, w_color, w_depth, w_median, w_var,
+                                               depth_scale, depth_mask)
+    return loss, [color, depth, median, var], [g_c, g_d, g_m, g_v]
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,

@@ -96,7 +96,7 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   with one list per warp (8x8 block); 0 = one pixel per lane, 8x4 blocks;
  *                   2 (default) = 3 (same results up to summation order).
  *   "bwd_occ"       CTAs per SM the quarter-list kernel is built for: 8 (64 registers) or 7 (72
- *                   registers); 0 (default) = 7 for -full, 8 for -light (measured best).
+ *                   registers, default: measured 5-9 % faster at C3 / C4).
  *   "async_binning" 1 (default): the forward sizes the binning buffer from the previous frame's
  *                   duplicate count (+25 %) and enqueues the scatter and the per-tile sort before
  *                   the host has read this frame's count, so the GPU does not idle during the
@@ -327,6 +327,29 @@ GSR_API int gsr_tracker_set_pose(gsr_tracker* t, const float* quat_wxyz, const f
  * caller_stream by the caller. */
 GSR_API int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iterations,
                             float* loss_history, gsr_track_result* result, void* caller_stream);
+
+/* ---- RGB-D L1 loss + cotangents (helper next to the hot path; not part of the reference surface) ----
+ * One pass over the rendered images of a frame:
+ *   L = w_color sum |C - C_gt| + w_depth sum_m |D - D_gt|
+ *       + (light) w_aux0 sum_m |D_median - D_gt| + w_aux1 sum depth_var
+ *       + (full)  w_aux0 sum (1 - O)                     (O = the "uncertainty" / accumulated-opacity output)
+ * m = 1, or (depth_mask != 0) the pixels with D_gt > 0.  Writes L to loss[0] (device) and the cotangent
+ * images dL/dC [3,H,W], dL/dD, dL/daux0, dL/daux1 (light only) [H,W] that gsr_*_backward consume as dL_dpix,
+ * dL_dpix_depth, dL_dpix_median_depth / dL_dpix_uncertainty, dL_dpix_depth_var.  The ground truth comes as
+ * fp32 ([3,H,W] colour, [H,W] depth) or in dataset formats: uint8 colour scaled by color_scale (1/255) and
+ * int16 depth scaled by depth_scale (1e-3 for millimetres).  The sum is formed in a fixed order
+ * (deterministic).  scratch: gsr_rgbd_l1_scratch_floats(width, height) floats of device memory. */
+typedef struct gsr_rgbd_l1 {
+  float w_color, w_depth, w_aux0, w_aux1;
+  float color_scale, depth_scale;
+  int depth_mask;
+} gsr_rgbd_l1;
+GSR_API size_t gsr_rgbd_l1_scratch_floats(int width, int height);
+GSR_API int gsr_rgbd_l1_loss(int variant /* 0 light, 1 full */, int width, int height,
+                             const float* color, const float* depth, const float* aux0, const float* aux1,
+                             const void* gt_color, int gt_color_is_u8, const void* gt_depth, int gt_depth_is_i16,
+                             const gsr_rgbd_l1* prm, float* dL_dcolor, float* dL_ddepth, float* dL_daux0,
+                             float* dL_daux1, float* loss, float* scratch, void* stream);
 
 /* replaces Rasterizer::markVisible (rasterizer.h:24-29): present[i] = view-space z > 0.2.
  * `present` is one byte per Gaussian (0/1). */

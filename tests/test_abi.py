@@ -104,6 +104,11 @@ def test_extension_entry_points_validate_arguments_without_a_gpu(built):
     assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, None, 1, None, None, None, None) == -1
     assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, f, 17, f, f, f, None) == -1   # more than 16 views
     assert lib.gsr_sh_grad_from_view_ptrs(0, 3, 16, None, 0, None, None, None, None) == 0
+    # RGB-D L1 loss helper
+    lib.gsr_rgbd_l1_scratch_floats.restype = ctypes.c_size_t
+    assert lib.gsr_rgbd_l1_scratch_floats(1920, 1080) >= 1920 * 1080 // 256
+    assert lib.gsr_rgbd_l1_loss(1, 16, 16, None, f, f, f, f, 1, f, 1, f, f, f, f, f, f, f, None) == -1
+    assert lib.gsr_rgbd_l1_loss(2, 16, 16, f, f, f, f, f, 1, f, 1, f, f, f, f, f, f, f, None) == -1
 
 
 @pytest.mark.parametrize("variant", ["light", "full"])

@@ -875,3 +875,58 @@ def test_densify_stats_match_torch_accumulation(built, variant):
     before = accum.clone()
     pu.run_variant(mod, variant, cam, scene, sc.make_cotangents(cam, _n_aux(variant), seed=20))
     assert torch.equal(before, accum)
+
+
+# ---- RGB-D L1 loss helper (extension) -----------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", ["light", "full"])
+@pytest.mark.parametrize("dataset_formats", [True, False])
+def test_rgbd_l1_loss_matches_torch(built, variant, dataset_formats):
+    """rgbd_l1_loss: loss value and every cotangent image equal the same loss written with torch ops,
+    for uint8 / int16 ground truth (dataset formats) and fp32 ground truth, with and without the depth
+    mask; driving the backward with the returned cotangents gives the same gradients as loss.backward()."""
+    sc, cam, scene = _scene(3000, 200, 120, seed=91, backdrop=(variant == "full"))
+    mod = built.load_variant(variant)
+    d = lambda t, rg=False: t.to(DEV).clone().requires_grad_(rg)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    gt_rgb_u8 = torch.randint(0, 256, (3, cam.H, cam.W), generator=g, dtype=torch.uint8)
+    gt_mm = (scene.gt_depth[0] * 1000.0).round().to(torch.int16)
+    gt_mm[::7, ::5] = 0                                        # invalid depth pixels
+    if dataset_formats:
+        gt_c, gt_d = gt_rgb_u8.to(DEV), gt_mm.to(DEV)
+    else:
+        gt_c, gt_d = (gt_rgb_u8.float() / 255.0).to(DEV), (gt_mm.float() * 1e-3).to(DEV)
+    ref_c, ref_d = gt_rgb_u8.float().to(DEV) * (1.0 / 255.0), (gt_mm.to(DEV) * 1e-3).unsqueeze(0)
+    for depth_mask in (False, True):
+        grads = []
+        for fused in (True, False):
+            P = dict(means3D=d(scene.means3D, True), shs=d(scene.shs, True), opacities=d(scene.opacities, True),
+                     scales=d(scene.scales, True), rotations=d(scene.rotations, True))
+            view = d(cam.viewmatrix, True)
+            rs = pu.settings_for(mod, variant, cam, scene, DEV)
+            res = mod.GaussianRasterizer(rs)(means3D=P["means3D"], means2D=torch.zeros_like(P["means3D"], requires_grad=True),
+                                             opacities=P["opacities"], shs=P["shs"], scales=P["scales"],
+                                             rotations=P["rotations"], viewmatrix=view, gt_depth=d(scene.gt_depth))
+            m = (ref_d > 0).float() if depth_mask else torch.ones_like(ref_d)
+            w = dict(w_color=0.7, w_depth=1.3)
+            if variant == "light":
+                w.update(w_median=0.4, w_var=0.2)
+                want = (0.7 * (res[0] - ref_c).abs().sum() + 1.3 * (m * (res[2] - ref_d).abs()).sum()
+                        + 0.4 * (m * (res[3] - ref_d).abs()).sum() + 0.2 * res[4].sum())
+            else:
+                w.update(w_silhouette=0.4)
+                want = (0.7 * (res[0] - ref_c).abs().sum() + 1.3 * (m * (res[2] - ref_d).abs()).sum()
+                        + 0.4 * (1.0 - res[3]).sum())
+            if fused:
+                loss, tensors, cots = mod.rgbd_l1_loss(res, gt_c, gt_d, depth_mask=depth_mask, **w)
+                assert abs(float(loss) - float(want)) <= 2e-5 * abs(float(want)), (float(loss), float(want))
+                auto = torch.autograd.grad(want, tensors, retain_graph=True)
+                for a_, c_ in zip(auto, cots):
+                    assert torch.equal(a_.reshape(-1), c_.reshape(-1))
+                torch.autograd.backward(tensors, cots)
+            else:
+                want.backward()
+            grads.append({k: v.grad.detach().cpu().numpy() for k, v in P.items()} | {"view": view.grad.cpu().numpy()})
+        for k in grads[0]:
+            rel, _ = pu.grad_mismatch(grads[0][k], grads[1][k], rtol=1e-4)
+            assert rel < 1e-4, (k, rel)
