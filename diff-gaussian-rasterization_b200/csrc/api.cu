@@ -24,7 +24,7 @@ std::atomic<long long> g_launches{0};
 // when it starts (OptionsCall), and everything below reads the snapshot: a concurrent
 // gsr_set_option from another thread can never change the switches in the middle of a call, and a
 // value one thread's call is using is never written by another thread.
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/1};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -93,6 +93,19 @@ StageScope::~StageScope() {
 }
 
 Options& options() { return t_opts; }
+
+void prefer_max_shared_once(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;   // (kernel, device) pairs already configured
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+  std::lock_guard<std::mutex> lk(mu);
+  for (const auto& d : done)
+    if (d.first == kernel && d.second == dev) return;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+    cudaGetLastError();
+  done.emplace_back(kernel, dev);
+}
 
 OptionsCall::OptionsCall(const char* entry_point) {
   t_opts = g_opts;
@@ -256,6 +269,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "bulk_sh")) return &g_opts.bulk_sh;
   if (!strcmp(key, "cnt_stride")) return &g_opts.cnt_stride;
   if (!strcmp(key, "bwd_occ")) return &g_opts.bwd_occ;
+  if (!strcmp(key, "fwd_packed")) return &g_opts.fwd_packed;
   return nullptr;
 }
 

@@ -53,6 +53,7 @@ struct Options {
   int bulk_sh;
   int cnt_stride;
   int bwd_occ;
+  int fwd_packed;
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the
@@ -87,6 +88,10 @@ struct StageScope {
   int slot;
   cudaStream_t stream;
 };
+
+// One-time (per kernel and device) request for the maximum shared-memory carve-out: the attribute call
+// takes a driver lock, so it is kept off the per-frame path.
+void prefer_max_shared_once(const void* kernel);
 
 // ---- error plumbing ------------------------------------------------------------------------
 void set_error(const char* fmt, ...);

@@ -606,8 +606,7 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   }
   {
 #define GSR_PRE_BWD(V, MT, TMA)                                                                  \
-  cudaFuncSetAttribute(preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1>,         \
-                       cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+  prefer_max_shared_once(reinterpret_cast<const void*>(&preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1>)); \
   preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1><<<blocks, kBwdThreads, smem, stream>>>( \
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \

@@ -397,8 +397,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
   const int blocks = (P + kPreThreads - 1) / kPreThreads;
   StageScope st(ST_PRE_FWD, stream);
 #define GSR_PRE_FWD(MT, TMA)                                                                     \
-  cudaFuncSetAttribute(preprocess_fwd_kernel<MT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, \
-                       cudaSharedmemCarveoutMaxShared);                                          \
+  prefer_max_shared_once(reinterpret_cast<const void*>(&preprocess_fwd_kernel<MT, TMA>));       \
   preprocess_fwd_kernel<MT, TMA><<<blocks, kPreThreads, smem, stream>>>(                         \
       P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,        \
       colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,  \

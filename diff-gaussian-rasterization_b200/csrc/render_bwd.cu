@@ -20,6 +20,7 @@
 //    the end of the list.
 // Bound: FP32 issue + shuffle + L2 atomics, not HBM.
 #include "gsr_common.cuh"
+#include "f32x2.cuh"
 
 namespace gsr {
 
@@ -49,42 +50,6 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return r;
 }
 
-typedef unsigned long long f2;  // two packed floats (lo = pixel row y0, hi = pixel row y0 + 1)
-
-__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
-  f2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
-  f2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
-  f2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ float f2_lo(f2 v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ float f2_hi(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
-
-// Shared-memory accesses of the warp reduction through precomputed 32-bit shared addresses (kept in
-// two registers across the entry loop, so that no address arithmetic is redone per entry).
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 // sum of 16 consecutive floats in shared memory (4 x LDS.128, a packed add tree, one scalar add)
 __device__ __forceinline__ float row16_sum(unsigned addr) {
   f2 a0, a1, b0, b1, c0, c1, d0, d1;
@@ -578,18 +543,6 @@ __device__ __forceinline__ float fast_exp(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
   return r;
-}
-// Opaque copy: the value stays in a register; without it the compiler rebuilds per-thread shared
-// addresses from threadIdx inside the hot loop (5-8 instructions each time it needs one).
-__device__ __forceinline__ unsigned pin_reg(unsigned v) {
-  unsigned r;
-  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
-  return r;
-}
-__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
-  unsigned v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
 }
 // sum of 8 consecutive floats in shared memory (2 x LDS.128)
 __device__ __forceinline__ float row8_sum(unsigned addr) {

@@ -130,6 +130,9 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      raster_settings)
 
 
+_ABSENT = torch.Tensor([])
+
+
 class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
@@ -149,7 +152,7 @@ class GaussianRasterizer(nn.Module):
         pair_given = scales is not None or rotations is not None
         if (pair_missing and cov3D_precomp is None) or (pair_given and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-        absent = torch.Tensor([])
+        absent = _ABSENT  # empty CPU tensor = "not provided", as upstream passes torch.Tensor([])
         shs = absent if shs is None else shs
         colors_precomp = absent if colors_precomp is None else colors_precomp
         scales = absent if scales is None else scales

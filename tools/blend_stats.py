@@ -66,12 +66,14 @@ def main():
     lx, ly = np.meshgrid(np.arange(16), np.arange(16))
     lx, ly = lx.reshape(-1), ly.reshape(-1)
     blk = {"8x8": (ly // 8) * 2 + lx // 8, "8x4": (ly // 4) * 2 + lx // 8, "4x4": (ly // 4) * 4 + lx // 4,
+           "4x2": (ly // 2) * 4 + lx // 4,
            "16x4": ly // 4, "16x8": ly // 8, "16x16": lx * 0}
     tot = dict(pairs=0, entries=0, walk=0)
     hits = {k: 0 for k in blk}; cands = {k: 0 for k in blk}
     paired = {"8x8|2x(8x4) halves: full iterations": 0, "8x8|2x(8x4) halves: all iterations": 0,
               "8x4|2x(4x4) halves: full iterations": 0, "8x4|2x(4x4) halves: all iterations": 0,
               "8x8|4x(4x4) quarters: full iterations": 0, "8x8|4x(4x4) quarters: all iterations": 0,
+              "8x4|4x(4x2) quarters (1 px / lane): full iterations": 0, "8x4|4x(4x2) quarters (1 px / lane): all iterations": 0,
               "8x8 hits containing a first contributor": 0}
     hist_valid = np.zeros(65, dtype=np.int64)
     t0 = time.time()
@@ -133,6 +135,18 @@ def main():
                 f_lo[:len(l_lo)] = hs[l_lo, lo]; f_hi[:len(l_hi)] = hs[l_hi, hi]
                 paired[key + ": full iterations"] += int((f_lo | f_hi).sum())
                 paired[key + ": all iterations"] += n
+        # scalar kernel, one pixel per lane: warp = 8x4 block, four quarter warps = 4x2 blocks
+        hs2, cs2 = per["4x2"]
+        for wq in range(8):   # 8x4 warp blocks: column wq % 2, row wq // 2 (4 rows each)
+            wx, wy = wq % 2, wq // 2
+            subs = [(wy * 2 + dr) * 4 + (wx * 2 + dc) for dr in range(2) for dc in range(2)]
+            lists = [np.nonzero(cs2[:, b])[0] for b in subs]
+            n = max(len(l) for l in lists)
+            full = np.zeros(n, dtype=bool)
+            for l, b in zip(lists, subs):
+                full[:len(l)] |= hs2[l, b]
+            paired["8x4|4x(4x2) quarters (1 px / lane): full iterations"] += int(full.sum())
+            paired["8x4|4x(4x2) quarters (1 px / lane): all iterations"] += n
         # four quarter warps (4x4 blocks) of an 8x8 warp block walking their own lists
         hs, cs = per["4x4"]
         first_pix = np.argmax(contrib, axis=0)   # front-most contributor per pixel (0 if none)
@@ -154,12 +168,12 @@ def main():
     print("sampled %d tiles (every %d) in %.1f s; numbers below are scaled to the whole frame" % (len(tiles), a.every, time.time() - t0))
     print("blended pairs NG = %.1f M, entries = %.2f M, walked entries = %.2f M" % (tot["pairs"] * scale / 1e6, tot["entries"] * scale / 1e6, tot["walk"] * scale / 1e6))
     for name in blk:
-        npix = {"8x8": 64, "8x4": 32, "4x4": 16, "16x4": 64, "16x8": 128, "16x16": 256}[name]
+        npix = {"8x8": 64, "8x4": 32, "4x4": 16, "4x2": 8, "16x4": 64, "16x8": 128, "16x16": 256}[name]
         print("block %-6s hits %.2f M  candidates (bbox) %.2f M  valid pixels per hit %.1f of %d (%.0f %%)" % (
             name, hits[name] * scale / 1e6, cands[name] * scale / 1e6, tot["pairs"] / max(1, hits[name]), npix,
             100.0 * tot["pairs"] / max(1, hits[name]) / npix))
     for k, v in paired.items():
-        print("%-44s %.2f M" % (k, v * scale / 1e6))
+        print("%-60s %.2f M" % (k, v * scale / 1e6))
     cum = np.cumsum(hist_valid) / max(1, hist_valid.sum())
     print("8x8 hits by number of valid pixels: <=4: %.0f %%, <=8: %.0f %%, <=16: %.0f %%, <=32: %.0f %%" % (
         100 * cum[4], 100 * cum[8], 100 * cum[16], 100 * cum[32]))
