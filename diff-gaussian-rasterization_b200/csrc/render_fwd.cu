@@ -513,8 +513,11 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
                             cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
-  // "fwd_packed": 1 (default) two pixels per lane + quarter-warp lists, 0 one pixel per lane + half-warp lists
-  if (options().fwd_packed != 0)
+  // "fwd_packed": 1 = two pixels per lane + quarter-warp lists, 0 = one pixel per lane + half-warp lists,
+  // 2 (default) = per variant: packed for -full (C3 0.263 vs 0.295 ms, C4 0.559 vs 0.581), scalar for -light
+  // (C3 0.324 vs 0.323, C4 0.697 vs 0.629: the branch-free packed body pays for -light's two extra channels
+  // and its stop-before-blending rule on every entry)
+  if (options().fwd_packed == 1)
     render_fwdq_kernel<kLight, false, false><<<grid, kFwdQThreads, 0, stream>>>(
         img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, out_color, out_depth,
         out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
@@ -537,7 +540,7 @@ int launch_render_fwd_light_loss(const Camera& cam, const GeomState& g, const Bi
                                  const FusedLoss& fl, cudaStream_t stream) {
   dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
-  if (options().fwd_packed != 0)
+  if (options().fwd_packed == 1)
     render_fwdq_kernel<kLight, true, false><<<grid, kFwdQThreads, 0, stream>>>(
         img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, fl.gt_depth, out_color, out_depth,
         out_alpha, out_median, out_var, nullptr, nullptr, img.n_contrib, nullptr, nullptr,

@@ -95,9 +95,9 @@ GSR_API size_t gsr_backward_scratch_floats(int P);
  *                   quarter warp (a 4x4 pixel block) walks its own entry list; 1 = the same arithmetic
  *                   with one list per warp (8x8 block); 0 = one pixel per lane, 8x4 blocks;
  *                   2 (default) = 3 (same results up to summation order).
- *   "fwd_packed"    forward blend kernel: 1 (default) = two pixels per lane, packed fp32x2 arithmetic,
- *                   quarter-warp entry lists; 0 = one pixel per lane, half-warp lists.  Bit-identical
- *                   images either way.
+ *   "fwd_packed"    forward blend kernel: 1 = two pixels per lane, packed fp32x2 arithmetic, quarter-warp
+ *                   entry lists; 0 = one pixel per lane, half-warp lists; 2 (default) = 1 for -full, 0 for
+ *                   -light (measured).  Bit-identical images either way.
  *   "bwd_occ"       CTAs per SM the quarter-list kernel is built for: 8 (64 registers) or 7 (72
  *                   registers, default: measured 5-9 % faster at C3 / C4).
  *   "async_binning" 1 (default): the forward sizes the binning buffer from the previous frame's
