@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--no-dp-check", action="store_true", help="N > 1: skip the gradient-sum check")
     ap.add_argument("--track-off", action="store_true", help="-light only: mapping mode (no pose gradient)")
     ap.add_argument("--map-off", action="store_true", help="-light only: tracking mode (pose gradient only)")
-    ap.add_argument("--dp-mode", default="auto", choices=["auto", "allreduce", "factorized_sh", "nvls"],
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "allreduce", "factorized_sh", "nvls", "p2p"],
                     help="gradient exchange at N > 1 (diff-gaussian-rasterization_b200/dp.py)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (gsr_set_option)")
     a = ap.parse_args()
@@ -692,8 +692,9 @@ def main():
         "stats": {"num_rendered": num_rendered, "num_related": num_related,
                   "mean_tile_list": (num_rendered / float(tiles)) if num_rendered else None,
                   "mean_valid_contributors_per_pixel": (num_related / float(W * H)) if num_related else None,
-                  "exchange": ("%s: %d MB of scene gradients per rank and step" % (
-                      reducer.mode, reducer.bytes_per_step() >> 20)) if reducer is not None else None},
+                  "exchange": ("%s%s: %d MB of scene gradients per rank and step" % (
+                      reducer.mode, (" (slice all-reduce: %s)" % reducer.nvls["slice"]) if getattr(reducer, "nvls", None) else "",
+                      reducer.bytes_per_step() >> 20)) if reducer is not None else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frame.h2d_bytes,
                 "d2h_bytes_per_step": frame.d2h_bytes, "ms_per_step": e2e_ms / a.steps,
                 "step_ms": spread(e2e_per_step),

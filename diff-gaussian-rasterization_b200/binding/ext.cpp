@@ -9,13 +9,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
   m.def("mark_visible", &markVisible);
   // extension (not in the reference): flat scene-gradient arena for view-level data parallelism
-  m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false);
+  m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false,
+        pybind11::arg("early_masked_color") = false);
+  m.def("wait_masked_color", &waitMaskedColor, pybind11::arg("stream"));
   m.def("arm_grad_arena", &armGradArena);
   m.def("sh_grad_from_views", &shGradFromViews);
   // extensions for the NVLS exchange of dp.py (mode "nvls"): P2P-reading SH rebuild, in-switch slice all-reduce
   m.def("sh_grad_from_view_ptrs", &shGradFromViewPtrs);
   m.def("nvls_allreduce_slice", &nvlsAllreduceSlice, pybind11::arg("multicast_ptr"), pybind11::arg("offset_floats"),
         pybind11::arg("count_floats"), pybind11::arg("rank"), pybind11::arg("world"), pybind11::arg("max_blocks") = 0);
+  m.def("p2p_allreduce_slice", &p2pAllreduceSlice, pybind11::arg("replica_ptrs"), pybind11::arg("offset_floats"),
+        pybind11::arg("count_floats"), pybind11::arg("rank"), pybind11::arg("max_blocks") = 0);
   // extension (not in the reference): in-kernel densification statistics
   // extension (not in the reference): RGB-D L1 loss + cotangents in one pass over the rendered images
   m.def("rgbd_l1_loss", &rgbdL1Loss);

@@ -55,6 +55,10 @@ torch::Tensor g_grad_arena;  // see setGradArena
 bool g_arena_armed = false;  // the arena takes the NEXT backward only (one-shot), see armGradArena
 torch::Tensor g_densify_accum, g_densify_denom, g_max_radii;  // see setDensifyStats
 bool g_arena_factorized = false;
+// factorized arena: masked colour gradient written right after the blend backward + event (gsr_backward_extras)
+bool g_arena_early = false;
+cudaEvent_t g_masked_ready = nullptr;   // recorded by the backward that took the arena
+bool g_masked_recorded = false;
 
 struct SceneGrads {
   torch::Tensor means3D, sh, opacity, scales, rotations;
@@ -218,17 +222,23 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dmeans3D = sg.means3D;
   torch::Tensor dL_dmeans2D = torch::empty({P, 3}, fopts);
   torch::Tensor dL_dcolors = torch::empty({P, 3}, fopts);
-  torch::Tensor dL_ddepths = torch::empty({P, 1}, fopts);
-  torch::Tensor dL_dconic = torch::empty({P, 2, 2}, fopts);
+  // dL/dconic and dL/ddepth are intermediates of the reference (written by its blend backward, read by its
+  // per-Gaussian backward, never returned): here they live in registers of the fused per-Gaussian kernel
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
-  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr};
+  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr, nullptr};
   fill_densify(extras, P, means3D);
   if (sg.factorized) {
     extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
     extras.skip_sh_grad = 1;
     g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
+    if (g_arena_early && sh.numel() != 0 && !map_off) {
+      if (g_masked_ready == nullptr)
+        TORCH_CHECK(cudaEventCreateWithFlags(&g_masked_ready, cudaEventDisableTiming) == cudaSuccess, "cudaEventCreate failed");
+      extras.masked_color_ready_event = g_masked_ready;
+      g_masked_recorded = true;
+    }
   }
   torch::Tensor dL_dscales = sg.scales;
   torch::Tensor dL_drotations = sg.rotations;
@@ -253,8 +263,8 @@ RasterizeGaussiansBackwardCUDA(
       scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(pm), fptr(cp), tan_fovx, tan_fovy,
       P ? rad.data_ptr<int>() : nullptr, reinterpret_cast<char*>(gb.data_ptr()),
       reinterpret_cast<char*>(bb.data_ptr()), reinterpret_cast<char*>(ib.data_ptr()), fptr(gc),
-      fptr(gd), fptr(gm), fptr(gv), dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(),
-      dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), dL_ddepths.data_ptr<float>(),
+      fptr(gd), fptr(gm), fptr(gv), dL_dmeans2D.data_ptr<float>(), nullptr,
+      dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), nullptr,
       dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), fptr_mut(dL_dsh),
       dL_dscales.data_ptr<float>(), dL_drotations.data_ptr<float>(), debug ? 1 : 0, fptr(per),
       dL_dview.data_ptr<float>(), fptr(gtd), track_off ? 1 : 0, map_off ? 1 : 0,
@@ -345,17 +355,21 @@ RasterizeGaussiansBackwardCUDA(
   torch::Tensor dL_dmeans3D = sg.means3D;
   torch::Tensor dL_dmeans2D = torch::empty({P, 3}, fopts);
   torch::Tensor dL_dcolors = torch::empty({P, 3}, fopts);
-  torch::Tensor dL_dgau_depths = torch::empty({P, 1}, fopts);
-  torch::Tensor dL_dconic = torch::empty({P, 2, 2}, fopts);
   torch::Tensor dL_dopacity = sg.opacity;
   torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
-  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr};
+  gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr, nullptr};
   fill_densify(extras, P, means3D);
   if (sg.factorized) {
     extras.dL_dcolor_masked = sg.masked_color.data_ptr<float>();
     extras.skip_sh_grad = 1;
     g_grad_arena.narrow(0, (int64_t)P * 3, 3).copy_(campos.reshape({-1}).narrow(0, 0, 3), /*non_blocking=*/true);
+    if (g_arena_early && sh.numel() != 0) {
+      if (g_masked_ready == nullptr)
+        TORCH_CHECK(cudaEventCreateWithFlags(&g_masked_ready, cudaEventDisableTiming) == cudaSuccess, "cudaEventCreate failed");
+      extras.masked_color_ready_event = g_masked_ready;
+      g_masked_recorded = true;
+    }
   }
   torch::Tensor dL_dscales = sg.scales;
   torch::Tensor dL_drotations = sg.rotations;
@@ -379,8 +393,8 @@ RasterizeGaussiansBackwardCUDA(
       fptr(rot), fptr(cov), fptr(vm), fptr(pm), fptr(cp), tan_fovx, tan_fovy,
       P ? rad.data_ptr<int>() : nullptr, reinterpret_cast<char*>(gb.data_ptr()),
       reinterpret_cast<char*>(bb.data_ptr()), reinterpret_cast<char*>(ib.data_ptr()), fptr(gc),
-      fptr(gd), fptr(gu), dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(),
-      dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), dL_dgau_depths.data_ptr<float>(),
+      fptr(gd), fptr(gu), dL_dmeans2D.data_ptr<float>(), nullptr,
+      dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), nullptr,
       dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), fptr_mut(dL_dsh),
       dL_dscales.data_ptr<float>(), dL_drotations.data_ptr<float>(), fptr(per),
       dL_dview.data_ptr<float>(), fptr(gtd), scratch.data_ptr<float>(),
@@ -416,8 +430,10 @@ void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom
   }
 }
 
-void setGradArena(const torch::Tensor& arena, bool factorized_sh) {
+void setGradArena(const torch::Tensor& arena, bool factorized_sh, bool early_masked_color) {
   g_arena_factorized = factorized_sh;
+  g_arena_early = factorized_sh && early_masked_color;
+  g_masked_recorded = false;
   if (!arena.defined() || arena.numel() == 0) {
     g_grad_arena = torch::Tensor();
     g_arena_factorized = false;
@@ -431,6 +447,17 @@ void setGradArena(const torch::Tensor& arena, bool factorized_sh) {
               "grad arena must be 16-byte aligned (the kernels write it with 128-bit stores)");
   g_grad_arena = arena;
   g_arena_armed = true;
+}
+
+// Makes `stream` (a cudaStream_t as an integer) wait until the masked colour gradient of the backward that took
+// the arena is complete (set_grad_arena(..., early_masked_color=True)); returns false — and does nothing — when no
+// such backward has run since the arena was armed, in which case the caller orders after the whole backward.
+bool waitMaskedColor(int64_t stream) {
+  if (!g_masked_recorded || g_masked_ready == nullptr) return false;
+  TORCH_CHECK(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), g_masked_ready, 0) == cudaSuccess,
+              "cudaStreamWaitEvent failed");
+  g_masked_recorded = false;
+  return true;
 }
 
 bool armGradArena() {
@@ -480,6 +507,16 @@ void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t co
                                           (size_t)count_floats, (int)rank, (int)world, (int)max_blocks,
                                           at::cuda::getCurrentCUDAStream().stream());
   check_rc(rc, "gsr_nvls_allreduce_slice");
+}
+
+void p2pAllreduceSlice(const std::vector<int64_t>& replica_ptrs, int64_t offset_floats, int64_t count_floats,
+                       int64_t rank, int64_t max_blocks) {
+  std::vector<float*> rp;
+  for (int64_t p : replica_ptrs) rp.push_back(reinterpret_cast<float*>(p));
+  const int rc = gsr_p2p_allreduce_slice(rp.data(), (size_t)offset_floats, (size_t)count_floats, (int)rank,
+                                         (int)rp.size(), (int)max_blocks,
+                                         at::cuda::getCurrentCUDAStream().stream());
+  check_rc(rc, "gsr_p2p_allreduce_slice");
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix,

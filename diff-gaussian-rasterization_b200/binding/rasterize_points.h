@@ -84,10 +84,13 @@ RasterizeGaussiansBackwardCUDA(
 // run while it is disarmed return fresh tensors, which autograd accumulates into .grad as usual — so
 // several backwards per exchange (several views per rank, a tracking pass on the same scene) add up
 // instead of clobbering each other.
-void setGradArena(const torch::Tensor& arena, bool factorized_sh);
+void setGradArena(const torch::Tensor& arena, bool factorized_sh, bool early_masked_color);
+bool waitMaskedColor(int64_t stream);
 bool armGradArena();
 torch::Tensor shGradFromViewPtrs(const torch::Tensor& means3D, const std::vector<int64_t>& dR_ptrs,
                                  const std::vector<int64_t>& campos_ptrs, const int degree, const int M);
+void p2pAllreduceSlice(const std::vector<int64_t>& replica_ptrs, int64_t offset_floats, int64_t count_floats,
+                       int64_t rank, int64_t max_blocks);
 void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t count_floats, int64_t rank,
                         int64_t world, int64_t max_blocks);
 void setDensifyStats(const torch::Tensor& grad_accum, const torch::Tensor& denom,

@@ -246,6 +246,52 @@ int rederive(int variant, int P, int R, int width, int height, char* geom_buffer
 
 using namespace gsr;
 
+namespace gsr {
+namespace {
+// masked colour gradient of one view, straight from the blend backward's accumulator lines:
+// dL/dRGB with the channels the forward clamped at 0 zeroed, zeros for culled Gaussians (what
+// preprocess_bwd writes into GaussGradOut::dL_dcolor_masked).  12 bytes out per Gaussian.
+__global__ void __launch_bounds__(256)
+masked_color_kernel(int P, const int* __restrict__ radii, const unsigned char* __restrict__ clamped,
+                    const float* __restrict__ acc, float* __restrict__ out) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= P) return;
+  float r = 0.f, g = 0.f, b = 0.f;
+  if (radii[idx] > 0) {
+    const float* line = acc + (size_t)idx * kAccStride;
+    const unsigned char cb = clamped[idx];
+    r = (cb & 1) ? 0.f : line[ACC_R];
+    g = (cb & 2) ? 0.f : line[ACC_G];
+    b = (cb & 4) ? 0.f : line[ACC_B];
+  }
+  out[3 * (size_t)idx] = r; out[3 * (size_t)idx + 1] = g; out[3 * (size_t)idx + 2] = b;
+}
+
+// extras -> GaussGradOut; with masked_color_ready_event: early kernel + event, the per-Gaussian kernel skips it
+int apply_extras(const gsr_backward_extras* extras, GaussGradOut& out, int P, const int* radii, const GeomState& g,
+                 const float* acc, bool have_sh, cudaStream_t s) {
+  if (extras == nullptr) return GSR_OK;
+  out.dL_dcolor_masked = extras->dL_dcolor_masked;
+  if (extras->skip_sh_grad) out.dL_dsh = nullptr;
+  if (extras->densify_grad_accum != nullptr && extras->densify_denom != nullptr) {
+    out.densify_grad_accum = extras->densify_grad_accum;
+    out.densify_denom = extras->densify_denom;
+  }
+  out.max_radii2D = extras->max_radii2D;
+  if (extras->masked_color_ready_event != nullptr && extras->dL_dcolor_masked != nullptr && have_sh) {
+    {
+      StageScope st(ST_PRE_BWD, s);
+      masked_color_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, radii, g.clamped, acc, extras->dL_dcolor_masked);
+      GSR_LAUNCH_OK(false, s);
+    }
+    GSR_CUDA_OK(cudaEventRecord((cudaEvent_t)extras->masked_color_ready_event, s));
+    out.dL_dcolor_masked = nullptr;
+  }
+  return GSR_OK;
+}
+}  // namespace
+}  // namespace gsr
+
 extern "C" {
 
 int gsr_abi_version(void) { return GSR_B200_ABI_VERSION; }
@@ -453,15 +499,8 @@ int gsr_light_backward(
   }
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
                    dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr};
-  if (extras != nullptr) {
-    out.dL_dcolor_masked = extras->dL_dcolor_masked;
-    if (extras->skip_sh_grad) out.dL_dsh = nullptr;
-    if (extras->densify_grad_accum != nullptr && extras->densify_denom != nullptr) {
-      out.densify_grad_accum = extras->densify_grad_accum;
-      out.densify_denom = extras->densify_denom;
-    }
-    out.max_radii2D = extras->max_radii2D;
-  }
+  rc = apply_extras(extras, out, P, radii, g, acc, shs != nullptr && want_gauss, s);
+  if (rc != GSR_OK) return rc;
   return launch_preprocess_bwd(kLight, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
                                out, want_gauss, want_pose, debug != 0, s, done_counter);
@@ -512,15 +551,8 @@ int gsr_full_backward(
   if (rc != GSR_OK) return rc;
   GaussGradOut out{dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
                    dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview, nullptr, nullptr, nullptr, nullptr};
-  if (extras != nullptr) {
-    out.dL_dcolor_masked = extras->dL_dcolor_masked;
-    if (extras->skip_sh_grad) out.dL_dsh = nullptr;
-    if (extras->densify_grad_accum != nullptr && extras->densify_denom != nullptr) {
-      out.densify_grad_accum = extras->densify_grad_accum;
-      out.densify_denom = extras->densify_denom;
-    }
-    out.max_radii2D = extras->max_radii2D;
-  }
+  rc = apply_extras(extras, out, P, radii, g, acc, shs != nullptr, s);
+  if (rc != GSR_OK) return rc;
   return launch_preprocess_bwd(kFull, P, D, M, means3D, radii, shs, scales, rotations,
                                scale_modifier, cov3D_precomp, cam, perspec_matrix, g, acc, partials,
                                out, true, true, false, s, done_counter);

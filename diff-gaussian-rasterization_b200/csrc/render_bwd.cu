@@ -795,6 +795,316 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   }
 }
 
+
+// =================================================================================================
+// Octet variant: FOUR vertically adjacent pixels per lane (two fp32x2 pairs), a 4-lane group = a 4x4
+// pixel block, a warp = a 16x8 half tile whose EIGHT groups walk their own compacted entry lists side
+// by side; one warp per CTA (no block-level barrier at all, every warp stages its tile's entries itself).
+// Why: the quarter-list kernel spends ~171 instructions per list iteration for 64 pixel slots; most of
+// that is per-lane fixed cost (list fetch, entry loads, predicates, the 13-slot store / reduce / red).
+// With four pixels per lane the same fixed cost covers 128 pixel slots: the packed arithmetic doubles,
+// the reduction and the scalar bookkeeping do not; eight 4x4 lists in lock step need 1.22 M iterations
+// per C3 frame against 2.33 M (tools/blend_stats.py).  The per-pixel arithmetic (power, alpha, skip
+// decisions) is the quarter-list kernel's, instruction for instruction.
+// =================================================================================================
+constexpr int kBwdOBatch = 64;  // entries staged per round: two per lane
+constexpr int kBwdORow = 40;    // floats per reduction row: 160 bytes = 32 mod 128 -> conflict-free LDS.128
+
+struct OctConst { f2 dLp0, dLp1, dLp2, dLd, dLv, ngt2, tfbg2; };
+struct OctState { f2 T2, Bc0, Bc1, Bc2, Bd, Bv; };
+
+// one pixel pair's share of an entry: updates the pair's state, adds its partial sums to v (ACCUM) or
+// initialises v with them
+template <int VARIANT, bool ACCUM>
+__device__ __forceinline__ void oct_pair(OctState& S, const OctConst& K, const f2 G2, const f2 alpha2, const f2 dx2,
+                                         const f2 dy2, const ulonglong2& e3, const ulonglong2& e4, const f2 fsel,
+                                         f2 (&v)[kRedVals]) {
+  const f2 one2 = f2_pack(1.f, 1.f), mone2 = f2_pack(-1.f, -1.f), two2 = f2_pack(2.f, 2.f);
+  const f2 om2 = f2_fma(alpha2, mone2, one2);  // 1 - alpha (>= 0.01)
+  const f2 inv2 = f2_pack(fast_rcp(f2_lo(om2)), fast_rcp(f2_hi(om2)));
+  S.T2 = f2_mul(S.T2, inv2);
+  const f2 aT2 = f2_mul(alpha2, S.T2);
+  const f2 d0 = f2_fma(S.Bc0, mone2, e3.y), d1 = f2_fma(S.Bc1, mone2, e4.x), d2 = f2_fma(S.Bc2, mone2, e4.y);
+  const f2 dgt2 = f2_add(e3.x, K.ngt2);
+  const f2 cvar2 = f2_mul(dgt2, dgt2);
+  const f2 dd = f2_fma(S.Bd, mone2, e3.x), dv = f2_fma(S.Bv, mone2, cvar2);
+  const f2 colour_part = f2_fma(d2, K.dLp2, f2_fma(d1, K.dLp1, f2_mul(d0, K.dLp0)));
+  const f2 depth_part = f2_mul(dd, K.dLd);
+  f2 dLa = f2_fma(dv, K.dLv, f2_add(colour_part, depth_part));
+  S.Bc0 = f2_fma(alpha2, d0, S.Bc0);
+  S.Bc1 = f2_fma(alpha2, d1, S.Bc1);
+  S.Bc2 = f2_fma(alpha2, d2, S.Bc2);
+  S.Bd = f2_fma(alpha2, dd, S.Bd);
+  S.Bv = f2_fma(alpha2, dv, S.Bv);
+  const f2 aTd = f2_mul(aT2, K.dLd);
+  dLa = f2_fma(inv2, K.tfbg2, f2_mul(dLa, S.T2));
+  const f2 w2 = f2_mul(G2, dLa);
+  const f2 wx = f2_mul(w2, dx2), wy = f2_mul(w2, dy2);
+  const f2 dvar = f2_mul(f2_mul(aT2, dgt2), K.dLv);   // alpha T (depth - gt) dL/dvar
+  if (ACCUM) {
+    v[ACC_MX] = f2_add(v[ACC_MX], wx);
+    v[ACC_MY] = f2_add(v[ACC_MY], wy);
+    f2_fma_acc(v[ACC_CA], wx, dx2);
+    f2_fma_acc(v[ACC_CB], wx, dy2);
+    f2_fma_acc(v[ACC_CC], wy, dy2);
+    v[ACC_OP] = f2_add(v[ACC_OP], w2);
+    f2_fma_acc(v[ACC_R], aT2, K.dLp0);
+    f2_fma_acc(v[ACC_G], aT2, K.dLp1);
+    f2_fma_acc(v[ACC_B], aT2, K.dLp2);
+    v[ACC_DEPTH] = f2_add(v[ACC_DEPTH], f2_fma(dvar, two2, aTd));
+  } else {
+    v[ACC_MX] = wx;
+    v[ACC_MY] = wy;
+    v[ACC_CA] = f2_mul(wx, dx2);
+    v[ACC_CB] = f2_mul(wx, dy2);
+    v[ACC_CC] = f2_mul(wy, dy2);
+    v[ACC_OP] = w2;
+    v[ACC_R] = f2_mul(aT2, K.dLp0);
+    v[ACC_G] = f2_mul(aT2, K.dLp1);
+    v[ACC_B] = f2_mul(aT2, K.dLp2);
+    v[ACC_DEPTH] = f2_fma(dvar, two2, aTd);
+  }
+  if (VARIANT == kLight) {
+    if (ACCUM) {
+      v[ACC_PD] = f2_add(v[ACC_PD], aTd);
+    } else {
+      v[ACC_PD] = aTd;
+      v[ACC_MED] = 0ull;   // filled in by the caller (needs both pairs' restored T)
+      v[ACC_PGX] = 0ull;
+      v[ACC_PGY] = 0ull;
+    }
+  } else {
+    // pose terms of the reference's ComputePG (see render_bwdq_kernel)
+    const f2 pa = f2_mul(S.T2, f2_fma(fsel, depth_part, colour_part));
+    const f2 q = f2_mul(pa, G2);
+    if (ACCUM) {
+      f2_fma_acc(v[ACC_PD], fsel, aTd);
+      f2_fma_acc(v[ACC_PGX], q, dx2);
+      f2_fma_acc(v[ACC_PGY], q, dy2);
+    } else {
+      v[ACC_PD] = f2_mul(fsel, aTd);
+      v[ACC_PGX] = f2_mul(q, dx2);
+      v[ACC_PGY] = f2_mul(q, dy2);
+      v[ACC_MED] = 0ull;
+    }
+  }
+}
+
+// sum of 4 consecutive floats in shared memory (one LDS.128)
+__device__ __forceinline__ float row4_sum(unsigned addr) {
+  f2 a0, a1;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "r"(addr) : "memory");
+  const f2 t = f2_add(a0, a1);
+  return f2_lo(t) + f2_hi(t);
+}
+
+template <int VARIANT, bool POSE_ONLY>
+__global__ void __launch_bounds__(32, 16)
+render_bwdo_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
+                   const float4* __restrict__ rec, const float* __restrict__ bg,
+                   const float* __restrict__ gt_depth,
+                   const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
+                   const float* __restrict__ final_Ts,    // full
+                   const uint32_t* __restrict__ n_contrib,
+                   const uint32_t* __restrict__ first_contrib,  // full
+                   const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepths,
+                   const float* __restrict__ dL_dmedians,  // light
+                   const float* __restrict__ dL_dvars,     // light: depth_var, full: uncertainty
+                   float* __restrict__ acc) {
+  // staged entry, duplicated into pairs (layout of render_bwdq_kernel)
+  __shared__ ulonglong2 s_q[5][kBwdOBatch];
+  __shared__ int s_id[kBwdOBatch];
+  // entry lists of the eight groups, interleaved: byte [k][e] = k-th entry of group e
+  __shared__ __align__(16) unsigned char s_list[kBwdOBatch][8];
+  __shared__ __align__(16) float s_red[kRedVals][kBwdORow];
+
+  const int lane = threadIdx.x;
+  const int e = lane >> 2, l = lane & 3;     // group (4x4 block) and column inside it
+  reinterpret_cast<uint4*>(&s_list[0][0])[lane] = make_uint4(0u, 0u, 0u, 0u);   // 64 x 8 bytes = 32 x 16
+  const int tile_x = (int)blockIdx.x >> 1, half = (int)blockIdx.x & 1;          // half: rows 8 half .. 8 half + 7
+  const int tile = blockIdx.y * grid_x + tile_x;
+  const int px = tile_x * kTileX + (e & 3) * 4 + l;
+  const int py0 = blockIdx.y * kTileY + half * 8 + (e >> 2) * 4;
+  const bool in_x = px < W;
+  const uint32_t pix0 = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
+  const float pxf = (float)px;
+  const f2 npyA = f2_pack(-(float)py0, -(float)(py0 + 1)), npyB = f2_pack(-(float)(py0 + 2), -(float)(py0 + 3));
+  const float tile_x0 = (float)(tile_x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
+
+  const uint2 range = ranges[tile];
+  const int walk = (int)tile_last[tile];  // entries [0, walk) were used by some pixel
+  const int rounds = (walk + kBwdOBatch - 1) / kBwdOBatch;
+  const size_t HW = (size_t)H * (size_t)W;
+
+  float Tf[4], g0[4], g1[4], g2[4], gd[4], gv[4], gt[4], gm[4];
+  int lc[4], fm1[4];   // fm1: 0-based position of the front-most contributor
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    Tf[r] = g0[r] = g1[r] = g2[r] = gd[r] = gv[r] = gt[r] = gm[r] = 0.f;
+    lc[r] = 0; fm1[r] = -1;
+    if (in_x && py0 + r < H) {
+      const uint32_t pix = pix0 + (uint32_t)r * (uint32_t)W;
+      Tf[r] = (VARIANT == kLight) ? (1 - alphas[pix]) : final_Ts[pix];
+      lc[r] = (int)n_contrib[pix];
+      g0[r] = dL_dpix[pix]; g1[r] = dL_dpix[HW + pix]; g2[r] = dL_dpix[2 * HW + pix];
+      gd[r] = dL_ddepths[pix]; gv[r] = dL_dvars != nullptr ? dL_dvars[pix] : 0.f; gt[r] = gt_depth[pix];
+      if (VARIANT == kLight && dL_dmedians != nullptr) gm[r] = dL_dmedians[pix];
+      if (VARIANT == kFull) fm1[r] = (int)first_contrib[pix] - 1;
+    }
+  }
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  OctConst KA, KB;
+  KA.dLp0 = f2_pack(g0[0], g0[1]); KA.dLp1 = f2_pack(g1[0], g1[1]); KA.dLp2 = f2_pack(g2[0], g2[1]);
+  KA.dLd = f2_pack(gd[0], gd[1]); KA.dLv = f2_pack(gv[0], gv[1]); KA.ngt2 = f2_pack(-gt[0], -gt[1]);
+  KA.tfbg2 = f2_pack(-Tf[0] * (bg0 * g0[0] + bg1 * g1[0] + bg2 * g2[0]), -Tf[1] * (bg0 * g0[1] + bg1 * g1[1] + bg2 * g2[1]));
+  KB.dLp0 = f2_pack(g0[2], g0[3]); KB.dLp1 = f2_pack(g1[2], g1[3]); KB.dLp2 = f2_pack(g2[2], g2[3]);
+  KB.dLd = f2_pack(gd[2], gd[3]); KB.dLv = f2_pack(gv[2], gv[3]); KB.ngt2 = f2_pack(-gt[2], -gt[3]);
+  KB.tfbg2 = f2_pack(-Tf[2] * (bg0 * g0[2] + bg1 * g1[2] + bg2 * g2[2]), -Tf[3] * (bg0 * g0[3] + bg1 * g1[3] + bg2 * g2[3]));
+  OctState SA, SB;
+  SA.T2 = f2_pack(Tf[0], Tf[1]); SB.T2 = f2_pack(Tf[2], Tf[3]);
+  SA.Bc0 = SA.Bc1 = SA.Bc2 = SA.Bd = SA.Bv = 0ull;
+  SB.Bc0 = SB.Bc1 = SB.Bc2 = SB.Bd = SB.Bv = 0ull;
+  bool mid0 = true, mid1 = true, mid2 = true, mid3 = true;
+  const f2 mhalf2 = f2_pack(-0.5f, -0.5f);
+  using RS = RedSet<VARIANT, POSE_ONLY>;
+  constexpr unsigned kRowBytes = kBwdORow * 4;
+  const unsigned red_st = pin_reg(smem_u32(&s_red[0][lane]));
+  // reducing lane (e, l): slots l, l + 4, l + 8, l + 12 of its OWN group's four values
+  const unsigned red_ld = pin_reg(smem_u32(&s_red[l][4 * e]));
+  const unsigned list_w = pin_reg(smem_u32(&s_list[0][4 * (e >> 2)]));   // the word holding this group's byte
+  const unsigned qshift = pin_reg((unsigned)(e & 3) * 8u);
+  const unsigned gshift = pin_reg((unsigned)e * 4u);                     // this group's lanes in a ballot
+  const unsigned lt = (1u << lane) - 1u;
+  const int mshift = 8 * half;                                           // this warp's byte of block_mask16
+
+  for (int i = 0; i < rounds; ++i) {
+    __syncwarp();
+    // ---- stage 64 entries (two per lane), keep their block masks in registers -----------------------
+    unsigned m_s[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int t = lane + 32 * s2;
+      const int progress = i * kBwdOBatch + t;
+      m_s[s2] = 0u;
+      if (progress < walk) {
+        const int id = (int)point_list[range.x + (walk - progress - 1)];
+        const float4* r = rec + 3 * (size_t)id;
+        const float4 q0 = __ldg(r + 0), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+        s_id[t] = id;
+        m_s[s2] = (block_mask16(q0, q1, tile_x0, tile_y0) >> mshift) & 0xFFu;
+        s_q[0][t] = make_ulonglong2(f2_pack(q0.x, q1.z), f2_pack(q0.y, q0.y));
+        s_q[1][t] = make_ulonglong2(f2_pack(q0.z, q0.z), f2_pack(-q0.w, -q0.w));
+        s_q[2][t] = make_ulonglong2(f2_pack(q1.x, q1.x), f2_pack(q1.y, q2.w));
+        s_q[3][t] = make_ulonglong2(f2_pack(q1.w, q1.w), f2_pack(q2.x, q2.x));
+        s_q[4][t] = make_ulonglong2(f2_pack(q2.y, q2.y), f2_pack(q2.z, q2.z));
+      }
+    }
+    // ---- per-group compaction: entries whose cut ellipse can touch the group's 4x4 block ------------
+    int c[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) c[b] = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool hit = (m_s[s2] >> b) & 1u;
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[c[b] + __popc(ball & lt)][b] = (unsigned char)(lane + 32 * s2);
+        c[b] += __popc(ball);
+      }
+    }
+    __syncwarp();
+    int cnt = c[0], cnt_max = c[0];
+#pragma unroll
+    for (int b = 1; b < 8; ++b) {
+      cnt = (e == b) ? c[b] : cnt;
+      cnt_max = max(cnt_max, c[b]);
+    }
+    const int posbase = walk - i * kBwdOBatch - 1;   // 0-based list position of staged entry j = posbase - j
+
+    for (int k = 0; k < cnt_max; ++k) {
+      const bool active = k < cnt;
+      const int j = (int)((lds_u32(list_w + 8u * (unsigned)k) >> qshift) & 0xFFu);
+      const int pos = posbase - j;
+      const ulonglong2* eq = &s_q[0][j];
+      const ulonglong2 e0 = eq[0], e1 = eq[kBwdOBatch], e2 = eq[2 * kBwdOBatch];
+      const float dx = GSR_SUB(f2_lo(e0.x), pxf);
+      const float pc = f2_hi(e0.x);
+      const f2 dx2 = f2_pack(dx, dx);
+      const f2 dyA = f2_add(e0.y, npyA), dyB = f2_add(e0.y, npyB);
+      // pair_power for the four pixels, same rounding sequence as the forward
+      const f2 dxA = f2_mul(dx2, e1.x), dxB = f2_mul(dx2, e1.y);
+      const f2 qfA = f2_fma(dx2, dxA, f2_mul(dyA, f2_mul(dyA, e2.x)));
+      const f2 qfB = f2_fma(dx2, dxA, f2_mul(dyB, f2_mul(dyB, e2.x)));
+      const f2 pwA = f2_fma(qfA, mhalf2, f2_mul(dyA, dxB));
+      const f2 pwB = f2_fma(qfB, mhalf2, f2_mul(dyB, dxB));
+      const float p0 = f2_lo(pwA), p1 = f2_hi(pwA), p2 = f2_lo(pwB), p3 = f2_hi(pwB);
+      bool v0 = active && (pos < lc[0]) && !(p0 > 0.0f) && !(p0 < pc);
+      bool v1 = active && (pos < lc[1]) && !(p1 > 0.0f) && !(p1 < pc);
+      bool v2 = active && (pos < lc[2]) && !(p2 > 0.0f) && !(p2 < pc);
+      bool v3 = active && (pos < lc[3]) && !(p3 > 0.0f) && !(p3 < pc);
+      if (!__any_sync(0xffffffffu, v0 || v1 || v2 || v3)) continue;
+      const float o = f2_lo(e2.y), ps = f2_hi(e2.y);
+      float G0 = fast_exp(p0), G1 = fast_exp(p1), G2 = fast_exp(p2), G3 = fast_exp(p3);
+      float a0 = pair_alpha(o, G0), a1 = pair_alpha(o, G1), a2 = pair_alpha(o, G2), a3 = pair_alpha(o, G3);
+      // the forward blended this pair iff min(0.99, o * expf(power)) >= 15/255: certain for power >=
+      // power_sure; the few pairs below it repeat the forward's exact evaluation (divergent, rare)
+      if ((v0 && p0 < ps) || (v1 && p1 < ps) || (v2 && p2 < ps) || (v3 && p3 < ps)) {
+        if (v0 && p0 < ps) { G0 = expf(p0); a0 = pair_alpha(o, G0); v0 = !(a0 < kAlphaMin); }
+        if (v1 && p1 < ps) { G1 = expf(p1); a1 = pair_alpha(o, G1); v1 = !(a1 < kAlphaMin); }
+        if (v2 && p2 < ps) { G2 = expf(p2); a2 = pair_alpha(o, G2); v2 = !(a2 < kAlphaMin); }
+        if (v3 && p3 < ps) { G3 = expf(p3); a3 = pair_alpha(o, G3); v3 = !(a3 < kAlphaMin); }
+      }
+      const unsigned vmask = __ballot_sync(0xffffffffu, v0 || v1 || v2 || v3);
+      if (vmask == 0u) continue;
+      if (!v0) { G0 = 0.f; a0 = 0.f; }
+      if (!v1) { G1 = 0.f; a1 = 0.f; }
+      if (!v2) { G2 = 0.f; a2 = 0.f; }
+      if (!v3) { G3 = 0.f; a3 = 0.f; }
+
+      const ulonglong2 e3 = eq[3 * kBwdOBatch], e4 = eq[4 * kBwdOBatch];
+      f2 fselA = 0ull, fselB = 0ull;
+      if (VARIANT == kFull) {
+        fselA = f2_pack((v0 & (pos == fm1[0])) ? 1.f : 0.f, (v1 & (pos == fm1[1])) ? 1.f : 0.f);
+        fselB = f2_pack((v2 & (pos == fm1[2])) ? 1.f : 0.f, (v3 & (pos == fm1[3])) ? 1.f : 0.f);
+      }
+      f2 v[kRedVals];
+      oct_pair<VARIANT, false>(SA, KA, f2_pack(G0, G1), f2_pack(a0, a1), dx2, dyA, e3, e4, fselA, v);
+      oct_pair<VARIANT, true>(SB, KB, f2_pack(G2, G3), f2_pack(a2, a3), dx2, dyB, e3, e4, fselB, v);
+      if (VARIANT == kLight) {
+        // median: the first valid entry met from the back whose restored T exceeds 0.5
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+        if (v0 && mid0 && f2_lo(SA.T2) > 0.5f) { m0 = gm[0]; mid0 = false; }
+        if (v1 && mid1 && f2_hi(SA.T2) > 0.5f) { m1 = gm[1]; mid1 = false; }
+        if (v2 && mid2 && f2_lo(SB.T2) > 0.5f) { m2 = gm[2]; mid2 = false; }
+        if (v3 && mid3 && f2_hi(SB.T2) > 0.5f) { m3 = gm[3]; mid3 = false; }
+        v[ACC_MED] = f2_pack(m0 + m2, m1 + m3);
+      }
+
+      // reduction through shared memory: every lane stores its four pixels' sum per slot, then lane (e, l)
+      // adds its own group's four values for slots l, l + 4, l + 8, l + 12 and issues the red into the
+      // group's Gaussian
+#pragma unroll
+      for (int qn = 0; qn < RS::N; ++qn)
+        sts_f32(red_st + qn * kRowBytes, f2_lo(v[RS::slot(qn)]) + f2_hi(v[RS::slot(qn)]));
+      __syncwarp();
+      if ((vmask >> gshift) & 0xFu) {
+        float* line = acc + (size_t)s_id[j] * kAccStride;
+        if (POSE_ONLY) {
+          if (l < RS::N) atomicAdd(line + RS::slot(l), row4_sum(red_ld));
+        } else {
+          float* dst = line + l;
+#pragma unroll
+          for (int p4 = 0; p4 < (RS::N + 3) / 4; ++p4)
+            if (4 * p4 + 4 <= RS::N || l + 4 * p4 < RS::N) atomicAdd(dst + 4 * p4, row4_sum(red_ld + 4 * p4 * kRowBytes));
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 }  // namespace
 
 int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const BinState& b,
@@ -809,6 +1119,7 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
   const int mode = options().bwd_packed;
   const bool quarter = mode == 3 || mode == 2;
   const bool packed = mode == 1;
+  const bool octet = mode == 4;
   // measured (C3 / C4, B200): -full 0.609 / 1.23 ms at 7 CTAs per SM (72 registers) vs 0.667 / 1.33 at 8 (the
   // 64-register build rematerialises shared addresses in the loop); -light 0.607 vs 0.620 at C3.
   // "bwd_occ" = 8 forces the 64-register build, anything else the 72-register one.
@@ -822,7 +1133,15 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
     if (occ7) render_bwdq_kernel<V, PO, 7><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC)); \
     else render_bwdq_kernel<V, PO, 8><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC));    \
   } while (0)
-  if (variant == kLight) {
+  const dim3 grid_o(2 * cam.grid_x, cam.grid_y, 1);   // octet kernel: one warp per half tile
+  if (octet) {
+    if (variant == kLight && pose_only)
+      render_bwdo_kernel<kLight, true><<<grid_o, 32, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
+    else if (variant == kLight)
+      render_bwdo_kernel<kLight, false><<<grid_o, 32, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));
+    else
+      render_bwdo_kernel<kFull, false><<<grid_o, 32, 0, stream>>>(GSR_BWD_ARGS(img.final_T, img.first_contrib));
+  } else if (variant == kLight) {
     if (quarter && pose_only)
       GSR_BWDQ(kLight, true, nullptr, nullptr);
     else if (quarter)

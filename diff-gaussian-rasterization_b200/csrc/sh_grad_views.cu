@@ -217,6 +217,60 @@ nvls_reduce_slice_kernel(float* __restrict__ mc, size_t begin4, size_t end4) {
   }
 }
 
+
+// ---- two-shot all-reduce of one slice over plain P2P loads / stores ---------------------------------
+// The same job as nvls_reduce_slice_kernel without the switch's reduction engine: a rank reads its 1/world
+// slice from every replica (peer pointers of the symmetric buffer), adds the replicas in rank order —
+// every element is summed by exactly one rank, so all ranks end up with bit-identical sums — and stores
+// the result into every replica.  world x 16 bytes are in flight per thread and unrolled step, so the
+// NVLink round trip (2-3 us) is covered by a few hundred KB per SM.
+struct PeerPtrs { float* p[kMaxPtrViews]; };
+
+__device__ __forceinline__ float4 ld_sys4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys4(float* p, const float4& v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+template <int WORLD, int UNROLL>
+__global__ void __launch_bounds__(256)
+p2p_reduce_slice_kernel(PeerPtrs pp, int world_rt, size_t begin4, size_t end4) {
+  const int world = WORLD > 0 ? WORLD : world_rt;
+  constexpr int WMAX = WORLD > 0 ? WORLD : kMaxPtrViews;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
+    float4 v[UNROLL][WMAX];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + u * stride;
+#pragma unroll
+      for (int r = 0; r < WMAX; ++r)
+        if (r < world && i < end4) v[u][r] = ld_sys4(pp.p[r] + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < end4) {
+        float4 s = v[u][0];
+#pragma unroll
+        for (int r = 1; r < WMAX; ++r)
+          if (r < world) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }
+#pragma unroll
+        for (int r = 0; r < WMAX; ++r)
+          if (r < world) st_sys4(pp.p[r] + 4 * i, s);
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace gsr
 
@@ -308,6 +362,49 @@ extern "C" int gsr_sh_grad_from_views(int P, int D, int M, const float* means3D,
     default: GSR_SH_VIEWS(0); break;
   }
 #undef GSR_SH_VIEWS
+  GSR_LAUNCH_OK(false, s);
+  return GSR_OK;
+}
+
+extern "C" int gsr_p2p_allreduce_slice(float* const* replica_ptrs, size_t offset_floats, size_t count_floats,
+                                       int rank, int world, int max_blocks, void* stream) {
+  using namespace gsr;
+  if (!replica_ptrs || world <= 0 || world > kMaxPtrViews || rank < 0 || rank >= world || (offset_floats & 3) ||
+      (count_floats & 3)) {
+    set_error("gsr_p2p_allreduce_slice: bad arguments (offset / count must be multiples of 4 floats, at most %d ranks)",
+              kMaxPtrViews);
+    return GSR_E_INVALID;
+  }
+  PeerPtrs pp;
+  for (int r = 0; r < kMaxPtrViews; ++r) {
+    pp.p[r] = r < world ? replica_ptrs[r] : nullptr;
+    if (r < world && (!pp.p[r] || (reinterpret_cast<uintptr_t>(pp.p[r]) & 15))) {
+      set_error("gsr_p2p_allreduce_slice: replica pointers must be non-NULL and 16-byte aligned");
+      return GSR_E_INVALID;
+    }
+  }
+  const size_t total4 = count_floats / 4;
+  const size_t per = (total4 + (size_t)world - 1) / (size_t)world;
+  const size_t b4 = offset_floats / 4 + per * (size_t)rank;
+  const size_t e4 = offset_floats / 4 + (per * (size_t)(rank + 1) < total4 ? per * (size_t)(rank + 1) : total4);
+  if (b4 >= e4) return GSR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = e4 - b4;
+  StageScope st(ST_OTHER, s);
+#define GSR_P2P(WT, UT)                                                                   \
+  do {                                                                                    \
+    const size_t want = (n + 256 * UT - 1) / (256 * UT);                                  \
+    int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);                     \
+    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;                       \
+    p2p_reduce_slice_kernel<WT, UT><<<blocks, 256, 0, s>>>(pp, world, b4, e4);            \
+  } while (0)
+  switch (world) {
+    case 2: GSR_P2P(2, 8); break;
+    case 4: GSR_P2P(4, 4); break;
+    case 8: GSR_P2P(8, 2); break;
+    default: GSR_P2P(0, 1); break;
+  }
+#undef GSR_P2P
   GSR_LAUNCH_OK(false, s);
   return GSR_OK;
 }

@@ -89,10 +89,14 @@ class SceneGradReducer:
                  sh_degree=3):
         """shapes: mapping name -> shape for the entries of PARAM_ORDER that exist.
         mode "factorized_sh" additionally needs the (replicated) means3D parameter tensor."""
-        assert mode in ("allreduce", "factorized_sh", "nvls")
+        assert mode in ("allreduce", "factorized_sh", "nvls", "p2p")
         self.group, self.average, self.mode = group, average, mode
         self.nvls = None
-        if mode == "nvls":
+        # "nvls": slice all-reduce in the switch (multimem) at 8 ranks and more, over plain P2P loads / stores
+        # below that (measured, tools/exchange_bench.py); "p2p": always the P2P slice all-reduce (no multicast
+        # needed).  GSR_DP_SLICE=nvls|p2p overrides the choice.
+        self._slice_kind = None if mode == "nvls" else ("p2p" if mode == "p2p" else None)
+        if mode in ("nvls", "p2p"):
             self.mode = mode = "factorized_sh"   # layout and SH rebuild are those of the factorized exchange
             self._nvls_requested = True
         else:
@@ -100,6 +104,8 @@ class SceneGradReducer:
         self.is_cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
         self._work, self._done, self._attached = None, None, None
+        import os
+        self._early, self._no_early = False, bool(os.environ.get("GSR_DP_NO_EARLY"))
         self.slices = OrderedDict()
         num = lambda shape: int(torch.Size(shape).numel())
         if mode == "allreduce":
@@ -143,16 +149,21 @@ class SceneGradReducer:
             group = self.group if self.group is not None else dist.group.WORLD
             flat = symm_mem.empty(self.numel, dtype=torch.float32, device=torch.device(device))
             hdl = symm_mem.rendezvous(flat, group)
-            if not int(hdl.multicast_ptr):
-                raise RuntimeError("no multicast support on this system")
+            import os
+            kind = os.environ.get("GSR_DP_SLICE") or self._slice_kind or ("nvls" if world >= 8 else "p2p")
+            if kind == "nvls" and not int(hdl.multicast_ptr):
+                if self._slice_kind is None and not os.environ.get("GSR_DP_SLICE"):
+                    kind = "p2p"
+                else:
+                    raise RuntimeError("no multicast support on this system")
+            self._slice_kind = kind
             flat.zero_()
             torch.cuda.synchronize(device)
             hdl.barrier(channel=0, timeout_ms=30000)
             torch.cuda.synchronize(device)
             self.flat = flat          # same layout as "factorized_sh": [dR 3P | campos 3 | pad | reduced 11P]
             self.nvls = dict(handle=hdl, world=world, rank=rank, mc=int(hdl.multicast_ptr),
-                             peers=[int(p) for p in hdl.buffer_ptrs])
-            import os
+                             peers=[int(p) for p in hdl.buffer_ptrs], slice=kind)
             if os.environ.get("GSR_DP_TIMING"):   # per-phase CUDA events, see nvls_timing()
                 self.nvls["timing"] = []
             self.mode = "nvls"
@@ -169,31 +180,39 @@ class SceneGradReducer:
         rows = [[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in t[5:]]
         return [sum(r[i] for r in rows) / max(1, len(rows)) for i in range(4)] if rows else None
 
-    def _nvls_exchange(self):
-        """Side stream, after the backward wrote this rank's gradients into its replica."""
+    def _nvls_exchange(self, cur, early):
+        """On self.stream.  `cur`: the stream the backward ran on.  early: self.stream has been ordered after the
+        masked colour gradient only (the per-Gaussian backward kernel may still be running on `cur`); else after
+        the whole backward."""
         n, C = self.nvls, self._attached._C
         timing = n.get("timing")
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timing is not None else None
         mark = (lambda i: ev[i].record()) if ev else (lambda i: None)
-        mark(0)
-        n["handle"].barrier(channel=0, timeout_ms=30000)        # every rank's gradients are in place
-        mark(1)
-        # the slice all-reduce (bound by switch round trips) and the P2P SH rebuild (bound by peer reads)
-        # are independent: they run side by side on two streams
         side = n.get("stream2")
         if side is None:
             side = n["stream2"] = torch.cuda.Stream(device=self.flat.device)
-        cur = torch.cuda.current_stream()
-        side.wait_stream(cur)
+        me = torch.cuda.current_stream()
+        mark(0)
+        n["handle"].barrier(channel=0, timeout_ms=30000)        # every rank's masked colour gradient is in place
+        mark(1)
+        # the slice all-reduce and the P2P SH rebuild are independent and both bound by the NVLink ports: they
+        # run side by side on two streams.  The all-reduce needs the peers' per-Gaussian backward kernels:
+        side.wait_stream(me)
+        if early:
+            side.wait_stream(cur)
         with torch.cuda.stream(side):
-            # a chain of switch round trips, not bandwidth: a few CTAs are enough, and they leave the
-            # SMs to the P2P SH rebuild that runs next to it
-            C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"],
-                                   max(16, 256 // n["world"]))
+            if early:
+                n["handle"].barrier(channel=2, timeout_ms=30000)    # every rank's 11 reduced floats are in place
+            # bound by the NVLink ports, not by parallelism (the time does not depend on the grid,
+            # tools/exchange_bench.py): a few CTAs are enough, and they leave the SMs to the SH rebuild
+            if n["slice"] == "p2p":
+                C.p2p_allreduce_slice(n["peers"], self.head, 11 * self.P, n["rank"], 37)
+            else:
+                C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"], 32)
         mark(2)
         self.sh_sum = C.sh_grad_from_view_ptrs(self.means3D.detach(), n["peers"],
                                                [p + 4 * 3 * self.P for p in n["peers"]], self.sh_degree, self.M)
-        cur.wait_stream(side)
+        me.wait_stream(side)
         mark(3)
         n["handle"].barrier(channel=1, timeout_ms=30000)        # all slices broadcast, all peer reads done
         mark(4)
@@ -214,7 +233,14 @@ class SceneGradReducer:
                 self.mode, self.nvls = "factorized_sh", None
             return False
         self._attached = rasterizer_module
-        fn(self.flat, self.mode in ("factorized_sh", "nvls"))
+        self._early = False
+        if self.mode == "nvls" and hasattr(rasterizer_module._C, "wait_masked_color") and not self._no_early:
+            # the masked colour gradient leaves the backward before its per-Gaussian kernel runs: the peers'
+            # reads of it (the SH rebuild) overlap that kernel
+            fn(self.flat, True, True)
+            self._early = True
+        else:
+            fn(self.flat, self.mode in ("factorized_sh", "nvls"))
         return True
 
     def detach(self):
@@ -299,10 +325,14 @@ class SceneGradReducer:
             self.pack(grads, masked_color, campos)
         extra_sh = grads.get("shs") if (grads is not None and self.mode in ("factorized_sh", "nvls")) else None
         if self.is_cuda:
-            self.stream.wait_stream(torch.cuda.current_stream())
+            cur = torch.cuda.current_stream()
+            early = bool(self.mode == "nvls" and self._early and extra_sh is None and
+                         self._attached._C.wait_masked_color(self.stream.cuda_stream))
+            if not early:
+                self.stream.wait_stream(cur)
             with torch.cuda.stream(self.stream):
                 if self.mode == "nvls":
-                    self._nvls_exchange()
+                    self._nvls_exchange(cur, early)
                 else:
                     self._exchange()
                 if extra_sh is not None:

@@ -154,6 +154,12 @@ typedef struct gsr_backward_extras {
   float* densify_grad_accum;
   float* densify_denom;
   float* max_radii2D;
+  /* View-parallel exchange (dp.py): when non-NULL (a cudaEvent_t) and dL_dcolor_masked is wanted, the masked
+   * colour gradient is written by a small kernel of its own right after the blend backward — before the
+   * per-Gaussian backward kernel runs — and this event is recorded on `stream` at that point, so that the
+   * caller can start gathering it from the peers underneath the per-Gaussian kernel.  NULL = written by the
+   * per-Gaussian kernel as before. */
+  void* masked_color_ready_event;
 } gsr_backward_extras;
 
 /* ---- light variant ---------------------------------------------------------------------- */
@@ -266,6 +272,14 @@ GSR_API int gsr_sh_grad_from_view_ptrs(int P, int D, int M, const float* means3D
  * not bandwidth bound, so a few CTAs are enough and the rest of the GPU stays free for a concurrent kernel). */
 GSR_API int gsr_nvls_allreduce_slice(float* multicast_ptr, size_t offset_floats, size_t count_floats,
                                      int rank, int world, int max_blocks, void* stream);
+
+/* The same slice all-reduce over plain P2P loads and stores (no multicast needed): replica_ptrs is a HOST array
+ * of `world` DEVICE pointers to the replicas of the symmetric buffer (entry `rank` is this rank's own).  The
+ * rank reads its 1/world slice from every replica, adds the replicas in rank order (all ranks obtain
+ * bit-identical sums) and stores the result into every replica.  All ranks call it between two barriers of
+ * their own.  offset / count: multiples of 4 floats; pointers 16-byte aligned; at most 16 ranks. */
+GSR_API int gsr_p2p_allreduce_slice(float* const* replica_ptrs, size_t offset_floats, size_t count_floats,
+                                    int rank, int world, int max_blocks, void* stream);
 
 /* ---- pose tracker (not part of the reference surface) ------------
  * K iterations of CG-SLAM's tracking loop — render(-light, map_off) -> masked L1 colour + depth loss

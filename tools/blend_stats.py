@@ -74,7 +74,10 @@ def main():
               "8x4|2x(4x4) halves: full iterations": 0, "8x4|2x(4x4) halves: all iterations": 0,
               "8x8|4x(4x4) quarters: full iterations": 0, "8x8|4x(4x4) quarters: all iterations": 0,
               "8x4|4x(4x2) quarters (1 px / lane): full iterations": 0, "8x4|4x(4x2) quarters (1 px / lane): all iterations": 0,
-              "8x8 hits containing a first contributor": 0}
+              "8x8 hits containing a first contributor": 0,
+              "16x8|8x(4x4) eighths (4 px / lane): full iterations": 0, "16x8|8x(4x4) eighths (4 px / lane): all iterations": 0,
+              "16x8|4x(8x4) quarters (4 px / lane): full iterations": 0, "16x8|4x(8x4) quarters (4 px / lane): all iterations": 0,
+              "8x16|8x(4x4) eighths (4 px / lane): full iterations": 0, "8x16|8x(4x4) eighths (4 px / lane): all iterations": 0}
     hist_valid = np.zeros(65, dtype=np.int64)
     t0 = time.time()
     for (tx, ty) in tiles:
@@ -164,6 +167,24 @@ def main():
             pix = blk["8x8"] == q
             fe = np.unique(first_pix[pix & has])
             paired["8x8 hits containing a first contributor"] += len(fe)
+        # a warp with FOUR pixels per lane: 16x8 (or 8x16) pixels, split into eight 4x4 blocks (4 lanes each) or four
+        # 8x4 blocks (8 lanes each), every block walking its own list
+        def lockstep(key, small, groups):
+            hs_, cs_ = per[small]
+            for subs in groups:
+                lists = [np.nonzero(cs_[:, b])[0] for b in subs]
+                n = max(len(l) for l in lists)
+                full = np.zeros(n, dtype=bool)
+                for l, b in zip(lists, subs):
+                    full[:len(l)] |= hs_[l, b]
+                paired[key + ": full iterations"] += int(full.sum())
+                paired[key + ": all iterations"] += n
+        # 4x4 block index = row4 * 4 + col4; 16x8 warp block = rows {2h, 2h+1} x all four columns
+        lockstep("16x8|8x(4x4) eighths (4 px / lane)", "4x4", [[(2 * h + r) * 4 + c for r in range(2) for c in range(4)] for h in range(2)])
+        # 8x16 warp block = all four rows x columns {2h, 2h+1}
+        lockstep("8x16|8x(4x4) eighths (4 px / lane)", "4x4", [[r * 4 + 2 * h + c for r in range(4) for c in range(2)] for h in range(2)])
+        # 8x4 block index = row4 * 2 + col8; 16x8 warp block = rows {2h, 2h+1} x both columns
+        lockstep("16x8|4x(8x4) quarters (4 px / lane)", "8x4", [[(2 * h + r) * 2 + c for r in range(2) for c in range(2)] for h in range(2)])
     scale = (gx * gy) / float(len(tiles))
     print("sampled %d tiles (every %d) in %.1f s; numbers below are scaled to the whole frame" % (len(tiles), a.every, time.time() - t0))
     print("blended pairs NG = %.1f M, entries = %.2f M, walked entries = %.2f M" % (tot["pairs"] * scale / 1e6, tot["entries"] * scale / 1e6, tot["walk"] * scale / 1e6))
