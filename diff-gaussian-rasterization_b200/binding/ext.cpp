@@ -7,6 +7,8 @@
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
   m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+  // extension: the same call + (want_colors_grad, want_cov3D_grad), see rasterize_points.cpp
+  m.def("rasterize_gaussians_backward_select", &RasterizeGaussiansBackwardSelect);
   m.def("mark_visible", &markVisible);
   // extension (not in the reference): flat scene-gradient arena for view-level data parallelism
   m.def("set_grad_arena", &setGradArena, pybind11::arg("arena"), pybind11::arg("factorized_sh") = false,
@@ -18,6 +20,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sh_grad_from_view_ptrs", &shGradFromViewPtrs);
   m.def("nvls_allreduce_slice", &nvlsAllreduceSlice, pybind11::arg("multicast_ptr"), pybind11::arg("offset_floats"),
         pybind11::arg("count_floats"), pybind11::arg("rank"), pybind11::arg("world"), pybind11::arg("max_blocks") = 0);
+  m.def("p2p_gather", &p2pGather, pybind11::arg("src_ptrs"), pybind11::arg("count_floats"), pybind11::arg("dst"),
+        pybind11::arg("max_blocks") = 0);
   m.def("p2p_allreduce_slice", &p2pAllreduceSlice, pybind11::arg("replica_ptrs"), pybind11::arg("offset_floats"),
         pybind11::arg("count_floats"), pybind11::arg("rank"), pybind11::arg("max_blocks") = 0);
   // extension (not in the reference): in-kernel densification statistics

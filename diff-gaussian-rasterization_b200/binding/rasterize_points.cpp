@@ -209,6 +209,30 @@ RasterizeGaussiansBackwardCUDA(
     const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
     const torch::Tensor& alphas, const bool debug, const torch::Tensor& perspec_matrix,
     const bool track_off, const bool map_off) {
+  return RasterizeGaussiansBackwardSelect(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                          cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                          dL_dout_depth, dL_dout_median_depth, dL_dout_depth_var, gt_depth, sh, degree,
+                                          campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, debug,
+                                          perspec_matrix, track_off, map_off, true, true);
+}
+
+// The same call with the two gradients autograd throws away when SH colours / scale + rotation are used
+// (dL/dcolors_precomp, dL/dcov3D_precomp: 36 bytes per Gaussian) made optional: not wanted -> not written, an
+// empty tensor is returned in their place.  The Python package passes ctx.needs_input_grad.
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardSelect(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+    const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_median_depth, const torch::Tensor& dL_dout_depth_var,
+    const torch::Tensor& gt_depth, const torch::Tensor& sh, const int degree,
+    const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+    const torch::Tensor& alphas, const bool debug, const torch::Tensor& perspec_matrix,
+    const bool track_off, const bool map_off, const bool want_colors_grad, const bool want_cov3D_grad) {
   const c10::cuda::CUDAGuard guard(means3D.device());
   const auto dev = means3D.device();
   const int P = means3D.size(0);
@@ -221,11 +245,11 @@ RasterizeGaussiansBackwardCUDA(
   SceneGrads sg = alloc_scene_grads(P, M, means3D, fopts);
   torch::Tensor dL_dmeans3D = sg.means3D;
   torch::Tensor dL_dmeans2D = torch::empty({P, 3}, fopts);
-  torch::Tensor dL_dcolors = torch::empty({P, 3}, fopts);
+  torch::Tensor dL_dcolors = torch::empty({want_colors_grad ? P : 0, 3}, fopts);
   // dL/dconic and dL/ddepth are intermediates of the reference (written by its blend backward, read by its
   // per-Gaussian backward, never returned): here they live in registers of the fused per-Gaussian kernel
   torch::Tensor dL_dopacity = sg.opacity;
-  torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
+  torch::Tensor dL_dcov3D = torch::empty({want_cov3D_grad ? P : 0, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
   gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr, nullptr};
   fill_densify(extras, P, means3D);
@@ -264,8 +288,8 @@ RasterizeGaussiansBackwardCUDA(
       P ? rad.data_ptr<int>() : nullptr, reinterpret_cast<char*>(gb.data_ptr()),
       reinterpret_cast<char*>(bb.data_ptr()), reinterpret_cast<char*>(ib.data_ptr()), fptr(gc),
       fptr(gd), fptr(gm), fptr(gv), dL_dmeans2D.data_ptr<float>(), nullptr,
-      dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), nullptr,
-      dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), fptr_mut(dL_dsh),
+      dL_dopacity.data_ptr<float>(), (want_colors_grad ? dL_dcolors.data_ptr<float>() : nullptr), nullptr,
+      dL_dmeans3D.data_ptr<float>(), (want_cov3D_grad ? dL_dcov3D.data_ptr<float>() : nullptr), fptr_mut(dL_dsh),
       dL_dscales.data_ptr<float>(), dL_drotations.data_ptr<float>(), debug ? 1 : 0, fptr(per),
       dL_dview.data_ptr<float>(), fptr(gtd), track_off ? 1 : 0, map_off ? 1 : 0,
       scratch.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream(), &extras);
@@ -341,6 +365,25 @@ RasterizeGaussiansBackwardCUDA(
     const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
     const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const int NG,
     const torch::Tensor& perspec_matrix) {
+  return RasterizeGaussiansBackwardSelect(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                          cov3D_precomp, viewmatrix, gt_depth, projmatrix, tan_fovx, tan_fovy,
+                                          dL_dout_color, dL_dout_depth, dL_dout_uncertainty, sh, degree, campos,
+                                          geomBuffer, R, binningBuffer, imageBuffer, NG, perspec_matrix, true, true);
+}
+
+// (see the -light variant: dL/dcolors_precomp and dL/dcov3D_precomp made optional)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardSelect(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+    const torch::Tensor& gt_depth, const torch::Tensor& projmatrix, const float tan_fovx,
+    const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_uncertainty, const torch::Tensor& sh, const int degree,
+    const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const int NG,
+    const torch::Tensor& perspec_matrix, const bool want_colors_grad, const bool want_cov3D_grad) {
   (void)NG;  // sized the reference's per-pair scratch lists; there are none here
   const c10::cuda::CUDAGuard guard(means3D.device());
   const auto dev = means3D.device();
@@ -354,9 +397,9 @@ RasterizeGaussiansBackwardCUDA(
   SceneGrads sg = alloc_scene_grads(P, M, means3D, fopts);
   torch::Tensor dL_dmeans3D = sg.means3D;
   torch::Tensor dL_dmeans2D = torch::empty({P, 3}, fopts);
-  torch::Tensor dL_dcolors = torch::empty({P, 3}, fopts);
+  torch::Tensor dL_dcolors = torch::empty({want_colors_grad ? P : 0, 3}, fopts);
   torch::Tensor dL_dopacity = sg.opacity;
-  torch::Tensor dL_dcov3D = torch::empty({P, 6}, fopts);
+  torch::Tensor dL_dcov3D = torch::empty({want_cov3D_grad ? P : 0, 6}, fopts);
   torch::Tensor dL_dsh = sg.sh;  // undefined in the factorized arena mode
   gsr_backward_extras extras{nullptr, 0, nullptr, nullptr, nullptr, nullptr};
   fill_densify(extras, P, means3D);
@@ -394,8 +437,8 @@ RasterizeGaussiansBackwardCUDA(
       P ? rad.data_ptr<int>() : nullptr, reinterpret_cast<char*>(gb.data_ptr()),
       reinterpret_cast<char*>(bb.data_ptr()), reinterpret_cast<char*>(ib.data_ptr()), fptr(gc),
       fptr(gd), fptr(gu), dL_dmeans2D.data_ptr<float>(), nullptr,
-      dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(), nullptr,
-      dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), fptr_mut(dL_dsh),
+      dL_dopacity.data_ptr<float>(), (want_colors_grad ? dL_dcolors.data_ptr<float>() : nullptr), nullptr,
+      dL_dmeans3D.data_ptr<float>(), (want_cov3D_grad ? dL_dcov3D.data_ptr<float>() : nullptr), fptr_mut(dL_dsh),
       dL_dscales.data_ptr<float>(), dL_drotations.data_ptr<float>(), fptr(per),
       dL_dview.data_ptr<float>(), fptr(gtd), scratch.data_ptr<float>(),
       at::cuda::getCurrentCUDAStream().stream(), &extras);
@@ -507,6 +550,18 @@ void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t co
                                           (size_t)count_floats, (int)rank, (int)world, (int)max_blocks,
                                           at::cuda::getCurrentCUDAStream().stream());
   check_rc(rc, "gsr_nvls_allreduce_slice");
+}
+
+void p2pGather(const std::vector<int64_t>& src_ptrs, int64_t count_floats, torch::Tensor& dst, int64_t max_blocks) {
+  TORCH_CHECK(dst.is_cuda() && dst.scalar_type() == torch::kFloat32 && dst.is_contiguous() && dst.dim() == 2 &&
+                  dst.size(0) == (int64_t)src_ptrs.size() && dst.size(1) >= count_floats,
+              "p2p_gather: dst must be a contiguous float32 CUDA tensor [nviews, >= count]");
+  const c10::cuda::CUDAGuard guard(dst.device());
+  std::vector<const float*> sp;
+  for (int64_t p : src_ptrs) sp.push_back(reinterpret_cast<const float*>(p));
+  const int rc = gsr_p2p_gather(sp.data(), (int)sp.size(), (size_t)count_floats, dst.data_ptr<float>(),
+                                (size_t)dst.size(1), (int)max_blocks, at::cuda::getCurrentCUDAStream().stream());
+  check_rc(rc, "gsr_p2p_gather");
 }
 
 void p2pAllreduceSlice(const std::vector<int64_t>& replica_ptrs, int64_t offset_floats, int64_t count_floats,

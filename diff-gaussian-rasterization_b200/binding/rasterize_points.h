@@ -38,6 +38,21 @@ RasterizeGaussiansBackwardCUDA(
     const torch::Tensor& alphas, const bool debug, const torch::Tensor& perspec_matrix,
     const bool track_off, const bool map_off);
 
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardSelect(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+    const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_median_depth, const torch::Tensor& dL_dout_depth_var,
+    const torch::Tensor& gt_depth, const torch::Tensor& sh, const int degree,
+    const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+    const torch::Tensor& alphas, const bool debug, const torch::Tensor& perspec_matrix,
+    const bool track_off, const bool map_off, const bool want_colors_grad, const bool want_cov3D_grad);
+
 #elif defined(GSR_VARIANT_FULL)
 
 std::tuple<int, int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
@@ -64,6 +79,19 @@ RasterizeGaussiansBackwardCUDA(
     const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const int NG,
     const torch::Tensor& perspec_matrix);
 
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardSelect(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+    const torch::Tensor& gt_depth, const torch::Tensor& projmatrix, const float tan_fovx,
+    const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_uncertainty, const torch::Tensor& sh, const int degree,
+    const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const int NG,
+    const torch::Tensor& perspec_matrix, const bool want_colors_grad, const bool want_cov3D_grad);
+
 #else
 #error "define GSR_VARIANT_LIGHT or GSR_VARIANT_FULL"
 #endif
@@ -89,6 +117,7 @@ bool waitMaskedColor(int64_t stream);
 bool armGradArena();
 torch::Tensor shGradFromViewPtrs(const torch::Tensor& means3D, const std::vector<int64_t>& dR_ptrs,
                                  const std::vector<int64_t>& campos_ptrs, const int degree, const int M);
+void p2pGather(const std::vector<int64_t>& src_ptrs, int64_t count_floats, torch::Tensor& dst, int64_t max_blocks);
 void p2pAllreduceSlice(const std::vector<int64_t>& replica_ptrs, int64_t offset_floats, int64_t count_floats,
                        int64_t rank, int64_t max_blocks);
 void nvlsAllreduceSlice(int64_t multicast_ptr, int64_t offset_floats, int64_t count_floats, int64_t rank,

@@ -24,7 +24,7 @@ std::atomic<long long> g_launches{0};
 // when it starts (OptionsCall), and everything below reads the snapshot: a concurrent
 // gsr_set_option from another thread can never change the switches in the middle of a call, and a
 // value one thread's call is using is never written by another thread.
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -192,7 +192,7 @@ Camera make_camera(const float* view, const float* proj, const float* campos, fl
 
 // shared front half of both forwards: allocate state, preprocess, bin
 int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinState& b,
-                  ImgState& img, int* num_rendered) {
+                  ImgState& img, int* num_rendered, SpecRender* spec = nullptr) {
   cam = make_camera(a.viewmatrix, a.projmatrix, a.cam_pos, a.tan_fovx, a.tan_fovy, a.width, a.height);
   const int HW = a.width * a.height;
   const int tiles = cam.grid_x * cam.grid_y;
@@ -225,7 +225,7 @@ int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinS
                                  a.prefiltered != 0, a.debug != 0, a.stream, a.gau_unc, a.gau_px);
   if (rc != GSR_OK) return rc;
   return run_binning(a.P, cam, a.radii, g, a.binning_alloc, a.binning_ctx, b, img, num_rendered,
-                     a.debug != 0, a.stream);
+                     a.debug != 0, a.stream, options().spec_render != 0 ? spec : nullptr);
 }
 
 int rederive(int variant, int P, int R, int width, int height, char* geom_buffer,
@@ -316,6 +316,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "cnt_stride")) return &g_opts.cnt_stride;
   if (!strcmp(key, "bwd_occ")) return &g_opts.bwd_occ;
   if (!strcmp(key, "fwd_packed")) return &g_opts.fwd_packed;
+  if (!strcmp(key, "spec_render")) return &g_opts.spec_render;
   return nullptr;
 }
 
@@ -391,11 +392,21 @@ int gsr_light_forward(
             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx,
             tan_fovy, prefiltered, gt_depth, radii, debug, s, gau_uncertainty, gau_related_pixels};
   Camera cam; GeomState g; BinState b; ImgState img;
-  rc = forward_front(a, kLight, cam, g, b, img, num_rendered);
+  SpecRender spec;
+  spec.launch = [&](const BinState& bs) {
+    return launch_render_fwd_light(cam, g, bs, img, background, gt_depth, out_color, out_depth, out_median_depth,
+                                   out_alpha, out_depth_var, gau_uncertainty, gau_related_pixels, debug != 0, s);
+  };
+  spec.reset = [&]() {   // the per-Gaussian statistics are accumulated with atomics by the blend
+    StageScope st(ST_MEMSET, s, 2);
+    GSR_CUDA_OK(cudaMemsetAsync(gau_uncertainty, 0, sizeof(float) * (size_t)P, s));
+    GSR_CUDA_OK(cudaMemsetAsync(gau_related_pixels, 0, sizeof(int) * (size_t)P, s));
+    return (int)GSR_OK;
+  };
+  rc = forward_front(a, kLight, cam, g, b, img, num_rendered, &spec);
   if (rc != GSR_OK) return rc;
-  return launch_render_fwd_light(cam, g, b, img, background, gt_depth, out_color, out_depth,
-                                 out_median_depth, out_alpha, out_depth_var, gau_uncertainty,
-                                 gau_related_pixels, debug != 0, s);
+  if (spec.done) return GSR_OK;
+  return spec.launch(b);
 }
 
 int gsr_full_forward(
@@ -433,12 +444,18 @@ int gsr_full_forward(
             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx,
             tan_fovy, prefiltered, gt_depth, radii, 0, s, nullptr, nullptr};
   Camera cam; GeomState g; BinState b; ImgState img;
-  rc = forward_front(a, kFull, cam, g, b, img, num_rendered);
-  if (rc != GSR_OK) return rc;
   const bool count = options().exact_ng != 0;
-  rc = launch_render_fwd_full(cam, g, b, img, background, out_color, out_depth, out_uncertainty,
-                              count, false, s);
+  SpecRender spec;
+  spec.launch = [&](const BinState& bs) {
+    return launch_render_fwd_full(cam, g, bs, img, background, out_color, out_depth, out_uncertainty, count, false, s);
+  };
+  spec.reset = []() { return (int)GSR_OK; };   // num_related is reset by the rescan of the redone binning
+  rc = forward_front(a, kFull, cam, g, b, img, num_rendered, &spec);
   if (rc != GSR_OK) return rc;
+  if (!spec.done) {
+    rc = spec.launch(b);
+    if (rc != GSR_OK) return rc;
+  }
   if (count) {
     uint32_t ng = 0;
     GSR_CUDA_OK(cudaMemcpyAsync(&ng, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -572,32 +572,43 @@ int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream
 
 int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gsr_alloc_fn alloc,
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
-                cudaStream_t stream) {
+                cudaStream_t stream, SpecRender* spec) {
   const int tiles = cam.grid_x * cam.grid_y;
   const bool tile_local = options().tile_sort != 0;
+  if (spec) spec->done = false;
   uint32_t N = 0, longest = 0;
   bool sorted_speculatively = false;
 
   if (tile_local) {
-    {
-      // img.tile_count was filled by preprocess_fwd (one red per duplicate)
-      StageScope st(ST_SCAN, stream, 1);
-      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
-                                                g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), true);
-      GSR_LAUNCH_OK(debug, stream);
-    }
     // The one host<->device synchronisation of the forward: the duplicate count sizes the binning
     // buffer and is returned to the caller (the reference blocks in the same place,
     // rasterizer_impl.cu:287).  To keep the GPU busy while the host waits, the count is copied into
-    // pinned memory asynchronously and — when a previous frame left a size estimate — the scatter
-    // and the per-tile sort are enqueued first, on a buffer sized from that estimate; the kernels
-    // are guarded, and if the estimate turns out too small the binning is simply redone.
+    // pinned memory asynchronously and — when a previous frame left a size estimate — the scatter,
+    // the per-tile sort and (spec) the forward blend are enqueued first, on a buffer sized from that
+    // estimate; the scan clamps the ranges to that buffer, the kernels are guarded, and if the estimate
+    // turns out too small the binning (and the blend) is simply redone.
     int device = 0;
     DeviceSlots* dsp = device_slots(&device);
     const bool slots_ok = dsp != nullptr && dsp->ok;
     uint32_t hint_n = 0, hint_l = 0;
     const bool speculate = slots_ok && options().async_binning != 0 &&
                            context_hint(device, cam.W, cam.H, P, &hint_n, &hint_l);
+    uint32_t cap = 0, lcap = 0, lpad = 0;
+    if (speculate) {
+      cap = spec_capacity(hint_n);
+      lcap = spec_longest(hint_l);
+      int p = kTileSortThreads;
+      while (p < (int)lcap) p <<= 1;
+      lpad = (uint32_t)p;   // the sort is launched for the next power of two
+    }
+    {
+      // img.tile_count was filled by preprocess_fwd (one red per duplicate)
+      StageScope st(ST_SCAN, stream, 1);
+      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, g.counters,
+                                                speculate ? cap : 0xFFFFFFFFu, speculate ? lpad : 0xFFFFFFFFu,
+                                                cnt_stride(), true);
+      GSR_LAUNCH_OK(debug, stream);
+    }
     uint32_t h[4] = {0, 0, 0, 0};
     if (slots_ok) {
       DeviceSlots& cs = *dsp;
@@ -605,24 +616,29 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
       uint32_t* hp = cs.host + 4 * slot;
       GSR_CUDA_OK(cudaMemcpyAsync(hp, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
       GSR_CUDA_OK(cudaEventRecord(cs.ev[slot], stream));
-      uint32_t cap = 0, lcap = 0;
       if (speculate) {
-        cap = spec_capacity(hint_n);
-        lcap = spec_longest(hint_l);
         const size_t need = BinState::carve(b, nullptr, cap, 0, false);
         char* chunk = alloc(alloc_ctx, need);
         if (chunk == nullptr) { set_error("binning allocator returned NULL for %zu bytes", need); return GSR_E_ALLOC; }
         BinState::carve(b, chunk, cap, 0, false);
-        const int rc = launch_tile_sort(cam, P, g, img, b, cap, lcap, debug, stream);
+        int rc = launch_tile_sort(cam, P, g, img, b, cap, lcap, debug, stream);
         if (rc != GSR_OK) return rc;
+        if (spec != nullptr) {
+          rc = spec->launch(b);
+          if (rc != GSR_OK) return rc;
+          spec->done = true;
+        }
       }
       GSR_CUDA_OK(cudaEventSynchronize(cs.ev[slot]));
       h[0] = hp[0]; h[2] = hp[2];
       if (speculate) {
-        int p = kTileSortThreads;
-        while (p < (int)lcap) p <<= 1;
-        sorted_speculatively = h[0] <= cap && h[2] <= (uint32_t)p;
+        sorted_speculatively = h[0] <= cap && h[2] <= lpad;
         if (!sorted_speculatively) {
+          if (spec != nullptr && spec->done) {
+            const int rc = spec->reset();
+            if (rc != GSR_OK) return rc;
+            spec->done = false;
+          }
           // estimate too small: reset the scatter cursors (the scan rewrites them) and fall through
           StageScope st(ST_SCAN, stream, 1);
           scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,

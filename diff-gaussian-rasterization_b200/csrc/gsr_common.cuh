@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <functional>
 #include <stdint.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -54,6 +55,7 @@ struct Options {
   int cnt_stride;
   int bwd_occ;
   int fwd_packed;
+  int spec_render;   // 1: forward blend enqueued before the host waits for the duplicate count
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the
@@ -492,9 +494,20 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
                           bool debug, cudaStream_t stream, float* zero_f32 = nullptr /* [P] or NULL */,
                           int* zero_i32 = nullptr /* [P] or NULL */);
 
+// Forward blend launched UNDERNEATH the count read-back (run_binning): when the binning is speculative
+// (buffer sized from the previous frame of this context), `launch` is called before the host waits for the
+// duplicate count, so that the device still has the scatter, the sort and the blend queued when the host
+// wakes up; if the estimate was too small the binning is redone, `reset` clears what the blend accumulates
+// and done is false again (the caller then launches the blend as usual).
+struct SpecRender {
+  std::function<int(const BinState&)> launch;
+  std::function<int()> reset;
+  bool done = false;
+};
 int run_binning(int P, const Camera& cam, const int* radii, GeomState& g, gsr_alloc_fn alloc,
                 void* alloc_ctx, BinState& b, ImgState& img, int* num_rendered, bool debug,
-                cudaStream_t stream);
+                cudaStream_t stream,
+                struct SpecRender* spec = nullptr);
 
 int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinState& b,
                             ImgState& img, const float* bg, const float* gt_depth,

@@ -271,6 +271,37 @@ p2p_reduce_slice_kernel(PeerPtrs pp, int world_rt, size_t begin4, size_t end4) {
   }
 }
 
+
+// ---- all-gather by P2P loads: every view's block is copied from its (peer) replica into a local buffer --------
+// A pure copy bound by the NVLink ports: a few CTAs with a deep queue of 128-bit loads are enough, so the kernel
+// can run UNDERNEATH the per-Gaussian backward kernel (dp.py launches it on a high-priority stream as soon as the
+// masked colour gradients exist) without taking the SMs from it.
+constexpr int kGatherUnroll = 8;
+__global__ void __launch_bounds__(256)
+p2p_gather_kernel(PeerPtrs src, int nviews, size_t count4, float* __restrict__ dst, size_t dst_stride4) {
+  const size_t total = (size_t)nviews * count4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kGatherUnroll) {
+    float4 v[kGatherUnroll];
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < total) {
+        const size_t view = i / count4, off = i - view * count4;
+        v[u] = ld_sys4(src.p[view] + 4 * off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < total) {
+        const size_t view = i / count4, off = i - view * count4;
+        reinterpret_cast<float4*>(dst)[view * dst_stride4 + off] = v[u];
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace gsr
 
@@ -405,6 +436,34 @@ extern "C" int gsr_p2p_allreduce_slice(float* const* replica_ptrs, size_t offset
     default: GSR_P2P(0, 1); break;
   }
 #undef GSR_P2P
+  GSR_LAUNCH_OK(false, s);
+  return GSR_OK;
+}
+
+extern "C" int gsr_p2p_gather(const float* const* src_ptrs, int nviews, size_t count_floats, float* dst,
+                              size_t dst_stride_floats, int max_blocks, void* stream) {
+  using namespace gsr;
+  if (!src_ptrs || !dst || nviews <= 0 || nviews > kMaxPtrViews || (count_floats & 3) || (dst_stride_floats & 3) ||
+      dst_stride_floats < count_floats || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_error("gsr_p2p_gather: bad arguments (count / stride must be multiples of 4 floats, at most %d views)", kMaxPtrViews);
+    return GSR_E_INVALID;
+  }
+  PeerPtrs pp;
+  for (int v = 0; v < kMaxPtrViews; ++v) {
+    pp.p[v] = v < nviews ? const_cast<float*>(src_ptrs[v]) : nullptr;
+    if (v < nviews && (!pp.p[v] || (reinterpret_cast<uintptr_t>(pp.p[v]) & 15))) {
+      set_error("gsr_p2p_gather: source pointers must be non-NULL and 16-byte aligned");
+      return GSR_E_INVALID;
+    }
+  }
+  if (count_floats == 0) return GSR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t total = (size_t)nviews * (count_floats / 4);
+  const size_t want = (total + 256 * kGatherUnroll - 1) / (256 * kGatherUnroll);
+  int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
+  StageScope st(ST_OTHER, s);
+  p2p_gather_kernel<<<blocks, 256, 0, s>>>(pp, nviews, count_floats / 4, dst, dst_stride_floats / 4);
   GSR_LAUNCH_OK(false, s);
   return GSR_OK;
 }

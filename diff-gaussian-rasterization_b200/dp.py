@@ -102,10 +102,15 @@ class SceneGradReducer:
         else:
             self._nvls_requested = False
         self.is_cuda = torch.device(device).type == "cuda"
-        self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
+        # high priority: the exchange kernels are small and mostly wait for NVLink; when they are launched
+        # underneath the per-Gaussian backward kernel they must not queue behind its CTAs
+        self.stream = torch.cuda.Stream(device=device, priority=-1) if self.is_cuda else None
         self._work, self._done, self._attached = None, None, None
         import os
+        # the early gather pays from 4 ranks on (the gathered volume grows with the rank count; measured equal at 2)
         self._early, self._no_early = False, bool(os.environ.get("GSR_DP_NO_EARLY"))
+        self._early_min_world = int(os.environ.get("GSR_DP_EARLY_MIN_WORLD", "4"))
+        self._gather_blocks = int(os.environ.get("GSR_DP_GATHER_BLOCKS", "74"))
         self.slices = OrderedDict()
         num = lambda shape: int(torch.Size(shape).numel())
         if mode == "allreduce":
@@ -190,28 +195,35 @@ class SceneGradReducer:
         mark = (lambda i: ev[i].record()) if ev else (lambda i: None)
         side = n.get("stream2")
         if side is None:
-            side = n["stream2"] = torch.cuda.Stream(device=self.flat.device)
+            side = n["stream2"] = torch.cuda.Stream(device=self.flat.device, priority=-1)
         me = torch.cuda.current_stream()
         mark(0)
         n["handle"].barrier(channel=0, timeout_ms=30000)        # every rank's masked colour gradient is in place
         mark(1)
-        # the slice all-reduce and the P2P SH rebuild are independent and both bound by the NVLink ports: they
-        # run side by side on two streams.  The all-reduce needs the peers' per-Gaussian backward kernels:
-        side.wait_stream(me)
         if early:
-            side.wait_stream(cur)
+            # all-gather of the masked colour gradients (+ camera positions) by P2P loads UNDERNEATH the
+            # per-Gaussian backward kernel: a pure copy bound by the NVLink ports, a few CTAs are enough
+            if self.gathered is None or self.gathered.shape[0] != n["world"]:
+                self.gathered = torch.empty(n["world"], self.head, dtype=torch.float32, device=self.flat.device)
+            C.p2p_gather(n["peers"], self.head, self.gathered, self._gather_blocks)
+            me.wait_stream(cur)                                  # this rank's per-Gaussian backward kernel is done
+            n["handle"].barrier(channel=2, timeout_ms=30000)     # ... and every rank's: the 11 reduced floats are in place
+        # the slice all-reduce (bound by the NVLink ports) and the SH rebuild (early: from the gathered copy, bound
+        # by HBM; else reading the peers in place) run side by side on two streams
+        side.wait_stream(me)
         with torch.cuda.stream(side):
-            if early:
-                n["handle"].barrier(channel=2, timeout_ms=30000)    # every rank's 11 reduced floats are in place
-            # bound by the NVLink ports, not by parallelism (the time does not depend on the grid,
-            # tools/exchange_bench.py): a few CTAs are enough, and they leave the SMs to the SH rebuild
+            # the time does not depend on the grid (tools/exchange_bench.py): a few CTAs are enough, and
+            # they leave the SMs to the SH rebuild
             if n["slice"] == "p2p":
                 C.p2p_allreduce_slice(n["peers"], self.head, 11 * self.P, n["rank"], 37)
             else:
                 C.nvls_allreduce_slice(n["mc"], self.head, 11 * self.P, n["rank"], n["world"], 32)
         mark(2)
-        self.sh_sum = C.sh_grad_from_view_ptrs(self.means3D.detach(), n["peers"],
-                                               [p + 4 * 3 * self.P for p in n["peers"]], self.sh_degree, self.M)
+        if early:
+            self.sh_sum = C.sh_grad_from_views(self.means3D.detach(), self.gathered, self.sh_degree, self.M)
+        else:
+            self.sh_sum = C.sh_grad_from_view_ptrs(self.means3D.detach(), n["peers"],
+                                                   [p + 4 * 3 * self.P for p in n["peers"]], self.sh_degree, self.M)
         me.wait_stream(side)
         mark(3)
         n["handle"].barrier(channel=1, timeout_ms=30000)        # all slices broadcast, all peer reads done
@@ -234,7 +246,8 @@ class SceneGradReducer:
             return False
         self._attached = rasterizer_module
         self._early = False
-        if self.mode == "nvls" and hasattr(rasterizer_module._C, "wait_masked_color") and not self._no_early:
+        if (self.mode == "nvls" and hasattr(rasterizer_module._C, "p2p_gather") and not self._no_early and
+                self.nvls["world"] >= self._early_min_world):
             # the masked colour gradient leaves the backward before its per-Gaussian kernel runs: the peers'
             # reads of it (the SH rebuild) overlap that kernel
             fn(self.flat, True, True)

@@ -57,14 +57,17 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, viewmatrix, radii, sh, geom,
          binning, img, gt_depth) = ctx.saved_tensors
+        # dL/dcolors_precomp and dL/dcov3Ds_precomp are only written when autograd wants them (with SH colours
+        # and scale + rotation it throws them away: 36 bytes per Gaussian of the per-Gaussian kernel's stores)
+        want_colors, want_cov = ctx.needs_input_grad[3], ctx.needs_input_grad[7]
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot,
-         g_view) = _C.rasterize_gaussians_backward(
+         g_view) = _C.rasterize_gaussians_backward_select(
             rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier,
             cov3Ds_precomp, viewmatrix, gt_depth, rs.projmatrix, rs.tanfovx, rs.tanfovy,
             grad_out_color, grad_out_depth, grad_out_uncertainty, sh, rs.sh_degree, rs.campos, geom,
-            ctx.num_rendered, binning, img, ctx.num_related_gaussians, rs.perspec_matrix)
-        return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, g_view,
-                None, None)
+            ctx.num_rendered, binning, img, ctx.num_related_gaussians, rs.perspec_matrix, want_colors, want_cov)
+        return (g_means3D, g_means2D, g_sh, g_colors if want_colors else None, g_opac, g_scales, g_rot,
+                g_cov3D if want_cov else None, g_view, None, None)
 
 
 def set_densify_stats(grad_accum=None, denom=None, max_radii2D=None):

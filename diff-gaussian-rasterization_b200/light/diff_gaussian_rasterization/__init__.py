@@ -88,8 +88,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                     grad_depth, grad_depth_median, grad_depth_var, gt_depth, sh, rs.sh_degree,
                     rs.campos, geom, ctx.num_rendered, binning, img, opacity_map, rs.debug,
                     rs.perspec_matrix, rs.track_off, rs.map_off)
+        # dL/dcolors_precomp and dL/dcov3Ds_precomp are only written when autograd wants them (with SH colours
+        # and scale + rotation it throws them away: 36 bytes per Gaussian of the per-Gaussian kernel's stores)
+        want_colors, want_cov = ctx.needs_input_grad[3], ctx.needs_input_grad[7]
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_view) = _guarded(
-            _C.rasterize_gaussians_backward, bwd_args, rs.debug, "snapshot_bw.dump", "backward")
+            _C.rasterize_gaussians_backward_select, bwd_args + (want_colors, want_cov), rs.debug,
+            "snapshot_bw.dump", "backward")
+        if not want_colors:
+            g_colors = None
+        if not want_cov:
+            g_cov3D = None
         # [1,4,4] here, already summed over pixels on the device ([H*W,4,4] + torch.sum upstream,
         # L/__init__.py:160): a view is enough, no reduction kernel
         g_view = g_view[0] if g_view.shape[0] == 1 else torch.sum(g_view, dim=0)

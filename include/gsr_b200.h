@@ -273,6 +273,13 @@ GSR_API int gsr_sh_grad_from_view_ptrs(int P, int D, int M, const float* means3D
 GSR_API int gsr_nvls_allreduce_slice(float* multicast_ptr, size_t offset_floats, size_t count_floats,
                                      int rank, int world, int max_blocks, void* stream);
 
+/* All-gather by P2P loads: copies count_floats floats from each of the nviews source pointers (HOST array of
+ * DEVICE pointers, typically the peers' replicas of a symmetric buffer) to dst + v * dst_stride_floats.  A pure
+ * copy bound by the NVLink ports; max_blocks > 0 confines it to that many CTAs so that it can run underneath
+ * another kernel.  count / stride: multiples of 4 floats; pointers 16-byte aligned; at most 16 views. */
+GSR_API int gsr_p2p_gather(const float* const* src_ptrs, int nviews, size_t count_floats, float* dst,
+                           size_t dst_stride_floats, int max_blocks, void* stream);
+
 /* The same slice all-reduce over plain P2P loads and stores (no multicast needed): replica_ptrs is a HOST array
  * of `world` DEVICE pointers to the replicas of the symmetric buffer (entry `rank` is this rank's own).  The
  * rank reads its 1/world slice from every replica, adds the replicas in rank order (all ranks obtain

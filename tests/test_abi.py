@@ -101,6 +101,9 @@ def test_extension_entry_points_validate_arguments_without_a_gpu(built):
     assert lib.gsr_nvls_allreduce_slice(None, ctypes.c_size_t(0), ctypes.c_size_t(16), 0, 2, 0, None) == -1
     assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(2), ctypes.c_size_t(16), 0, 2, 0, None) == -1
     assert lib.gsr_nvls_allreduce_slice(f, ctypes.c_size_t(0), ctypes.c_size_t(16), 2, 2, 0, None) == -1
+    assert lib.gsr_p2p_allreduce_slice(None, ctypes.c_size_t(0), ctypes.c_size_t(16), 0, 2, 0, None) == -1
+    assert lib.gsr_p2p_gather(None, 2, ctypes.c_size_t(16), f, ctypes.c_size_t(16), 0, None) == -1
+    assert lib.gsr_p2p_gather(f, 2, ctypes.c_size_t(18), f, ctypes.c_size_t(20), 0, None) == -1   # count not a multiple of 4
     assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, None, 1, None, None, None, None) == -1
     assert lib.gsr_sh_grad_from_view_ptrs(8, 3, 16, f, 17, f, f, f, None) == -1   # more than 16 views
     assert lib.gsr_sh_grad_from_view_ptrs(0, 3, 16, None, 0, None, None, None, None) == 0

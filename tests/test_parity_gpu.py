@@ -446,20 +446,23 @@ def test_packed_and_scalar_backward_kernels_agree(built, variant):
         assert rel < 2e-4 and bad < 1e-3, (k, rel, bad)
 
 
-def test_speculative_binning_overflow_is_redone(built):
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_speculative_binning_overflow_is_redone(built, variant):
     """async_binning sizes the binning buffer from the previous frame of the same (device, W, H, P)
-    context: a frame of small splats followed by one with many more duplicates (and much longer tile
-    lists) must redo the binning and stay exact; after a miss the context does not speculate until a
-    frame's counts would have fitted the previous estimate."""
+    context and enqueues the scatter, the sort AND the forward blend before the host has seen the
+    duplicate count: a frame of small splats followed by one with many more duplicates (and much longer
+    tile lists) must redo the binning and the blend (whose per-Gaussian statistics are atomics: a blend
+    that ran twice without the reset would count twice) and stay exact; after a miss the context does not
+    speculate until a frame's counts would have fitted the previous estimate."""
     sc = ge.load_scene_module()
-    mod = built.load_variant("light")
+    mod = built.load_variant(variant)
     cam = sc.make_camera(320, 240)
     small = sc.make_scene(30000, cam, (0.3, 0.6), seed=46)
     big = sc.make_scene(30000, cam, (2.0, 14.0), seed=47)
-    cot = sc.make_cotangents(cam, 3)
+    cot = sc.make_cotangents(cam, 3 if variant == "light" else 2)
     pu.set_option("async_binning", 0)
     try:
-        ref_o, ref_g = pu.run_variant(mod, "light", cam, big, cot)
+        ref_o, ref_g = pu.run_variant(mod, variant, cam, big, cot)
     finally:
         pu.set_option("async_binning", 1)
 
@@ -470,12 +473,54 @@ def test_speculative_binning_overflow_is_redone(built):
         for k in (ref_g if g is not None else {}):
             rel, _ = pu.grad_mismatch(g[k], ref_g[k], rtol=1e-4)
             assert rel < 1e-4, k
-    for _ in range(2):
-        pu.run_variant(mod, "light", cam, small, cot)      # leaves a small estimate behind ...
-        pu.run_variant(mod, "light", cam, small, cot)      # ... and marks the context stable
-        check(*pu.run_variant(mod, "light", cam, big, cot))  # speculates, overflows, is redone
-    for _ in range(3):                                     # estimate fits again: the speculative path
-        check(*pu.run_variant(mod, "light", cam, big, cot))
+    for spec_render in (1, 0):
+        pu.set_option("spec_render", spec_render)
+        try:
+            for _ in range(2):
+                pu.run_variant(mod, variant, cam, small, cot)      # leaves a small estimate behind ...
+                pu.run_variant(mod, variant, cam, small, cot)      # ... and marks the context stable
+                check(*pu.run_variant(mod, variant, cam, big, cot))  # speculates, overflows, is redone
+            for _ in range(3):                                     # estimate fits again: the speculative path
+                check(*pu.run_variant(mod, variant, cam, big, cot))
+        finally:
+            pu.set_option("spec_render", 1)
+
+
+def test_unwanted_gradients_are_not_written(built):
+    """With SH colours and scale + rotation autograd throws dL/dcolors_precomp and dL/dcov3Ds_precomp away:
+    the packages ask the backward not to write them (rasterize_gaussians_backward_select); the other
+    gradients are unchanged, and the reference-signature entry point still returns all of them."""
+    sc = ge.load_scene_module()
+    cam = sc.make_camera(160, 112)
+    scene = sc.make_scene(3000, cam, (1.0, 6.0), seed=5)
+    for variant in ("light", "full"):
+        mod = built.load_variant(variant)
+        cot = sc.make_cotangents(cam, 3 if variant == "light" else 2)
+        o, g = pu.run_variant(mod, variant, cam, scene, cot)
+        captured = {}
+        C = mod._C
+        orig = C.rasterize_gaussians_backward_select
+
+        def spy(*args):
+            captured["want"] = args[-2:]
+            full_out = orig(*args[:-2], True, True)
+            out = orig(*args)
+            captured["sizes"] = (tuple(out[1].shape), tuple(out[4].shape), tuple(full_out[1].shape), tuple(full_out[4].shape))
+            for i in (0, 2, 3, 5, 6, 7, 8):    # (two runs of the blend backward: atomics order differs)
+                rel, _ = pu.grad_mismatch(out[i].cpu().numpy(), full_out[i].cpu().numpy(), rtol=1e-4)
+                assert rel < 1e-4, i
+            return out
+        C.rasterize_gaussians_backward_select = spy
+        try:
+            o2, g2 = pu.run_variant(mod, variant, cam, scene, cot)
+        finally:
+            C.rasterize_gaussians_backward_select = orig
+        assert captured["want"] == (False, False)
+        P = scene.means3D.shape[0]
+        assert captured["sizes"] == ((0, 3), (0, 6), (P, 3), (P, 6))
+        for k in g:
+            rel, _ = pu.grad_mismatch(g2[k], g[k], rtol=1e-4)
+            assert rel < 1e-4, k
 
 
 def test_two_rasterizers_interleaved_on_two_streams(built):

@@ -91,6 +91,8 @@ def main():
     for b in (37, 74, 148, 296, 0):
         res["p2p b=%d" % b] = timed(lambda: C.p2p_allreduce_slice(peers, head, 11 * P, rank, b))
     res["sh_ptrs"] = timed(lambda: C.sh_grad_from_view_ptrs(means, peers, [p + 4 * 3 * P for p in peers], 3, M))
+    for b in (37, 74, 148, 0):
+        res["gather b=%d" % b] = timed(lambda: C.p2p_gather(peers, head, gathered, b))
     res["sh_local"] = timed(lambda: C.sh_grad_from_views(means, gathered, 3, M))
     res["nccl_ar"] = timed(lambda: dist.all_reduce(plain))
     res["nccl_ag"] = timed(lambda: dist.all_gather_into_tensor(gat_out, head_t))
