@@ -64,6 +64,7 @@ size_t ImgState::carve(ImgState& s, char* base, int HW, int tiles, int variant) 
   s.tile_last = c.take<uint32_t>((size_t)tiles);
   s.tile_count = c.take<uint32_t>((size_t)tiles * kCntStrideMax);
   s.tile_fill = c.take<uint32_t>((size_t)tiles * kCntStrideMax);
+  s.tile_order = c.take<uint32_t>((size_t)tiles);
   s.n_contrib = c.take<uint32_t>((size_t)HW);
   if (variant == kFull) {
     s.final_T = c.take<float>((size_t)HW);
@@ -76,6 +77,9 @@ size_t ImgState::carve(ImgState& s, char* base, int HW, int tiles, int variant) 
 }
 
 namespace {
+
+// tile_order is only produced when the blend kernels use it (option tile_lpt)
+inline uint32_t* tile_order_out(const ImgState& img) { return options().tile_lpt != 0 ? img.tile_order : nullptr; }
 
 // smallest b with (n >> b) == 0, i.e. the number of bits needed for tile ids < n
 // (same value the reference's getHigherMsb produces)
@@ -152,14 +156,24 @@ constexpr int kTileSortThreads = 256;
 // starts go back through shared memory to coalesced stores — 4 barriers per 8192 tiles.
 // reset_counters: this kernel is the first writer of the frame's counter block and initialises all of
 // it (no memset pass); the tracker passes false, its overflow flag is sticky across iterations.
+// tile_order: the tiles sorted by descending list length (counting sort over kOrderBins length classes of 16
+// entries; order inside a class is arbitrary): the blend kernels' CTA i takes tile tile_order[i], so the long
+// tiles start first and the short ones fill the tail of the kernel (gsr_common.cuh: tile_of_block).
 constexpr int kScanPer = 8;
+constexpr int kOrderBins = 256;
+__device__ __forceinline__ int order_bin(uint32_t count) {
+  const uint32_t c = count >> 4;
+  return (kOrderBins - 1) - (int)(c < (uint32_t)(kOrderBins - 1) ? c : (uint32_t)(kOrderBins - 1));
+}
 __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ counters,
+                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ tile_order,
+                  uint32_t* __restrict__ counters,
                   uint32_t capacity, uint32_t longest_cap, int cs, bool reset_counters) {
   __shared__ uint32_t s_cnt[1024 * (kScanPer + 1)];   // one pad word per 8: the stride-8 reads become stride 9
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry, s_max;
+  __shared__ uint32_t s_bin[kOrderBins];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto slot = [](int i) { return i + (i >> 3); };
   if (tid == 0) { s_carry = 0; s_max = 0; }
@@ -224,6 +238,30 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
   for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
   if (lane == 0) atomicMax(&s_max, local_max);
   __syncthreads();
+  if (tile_order != nullptr) {
+    // counting sort of the tiles by length class (the counts are L2-hot: this kernel just read them)
+    for (int b = tid; b < kOrderBins; b += 1024) s_bin[b] = 0u;
+    __syncthreads();
+    for (int t = tid; t < tiles; t += 1024) atomicAdd(&s_bin[order_bin(tile_count[(size_t)t * cs])], 1u);
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 256 class sizes: 8 per lane
+      uint32_t v8[kOrderBins / 32], sum8 = 0;
+#pragma unroll
+      for (int k = 0; k < kOrderBins / 32; ++k) { v8[k] = s_bin[lane * (kOrderBins / 32) + k]; sum8 += v8[k]; }
+      uint32_t inc8 = sum8;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc8, o);
+        if (lane >= o) inc8 += n;
+      }
+      uint32_t start8 = inc8 - sum8;
+#pragma unroll
+      for (int k = 0; k < kOrderBins / 32; ++k) { s_bin[lane * (kOrderBins / 32) + k] = start8; start8 += v8[k]; }
+    }
+    __syncthreads();
+    for (int t = tid; t < tiles; t += 1024)
+      tile_order[atomicAdd(&s_bin[order_bin(tile_count[(size_t)t * cs])], 1u)] = (uint32_t)t;
+  }
   if (tid == 0) {
     const bool cut = s_carry > capacity || s_max > longest_cap;
     counters[0] = s_carry;
@@ -554,7 +592,7 @@ int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgS
   if (longest_cap > (uint32_t)kTileSortCap) longest_cap = kTileSortCap;
   {
     StageScope st(ST_SCAN, stream, 1);
-    scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
+    scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, tile_order_out(img),
                                               g.counters, capacity, longest_cap, cnt_stride(), false);
     GSR_LAUNCH_OK(false, stream);
   }
@@ -565,7 +603,7 @@ int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgS
 // in g.counters[2] for the caller to read back.
 int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream_t stream) {
   scan_tiles_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges,
-                                            img.tile_fill, g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), false);
+                                            img.tile_fill, tile_order_out(img), g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), false);
   GSR_LAUNCH_OK(false, stream);
   return GSR_OK;
 }
@@ -604,7 +642,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     {
       // img.tile_count was filled by preprocess_fwd (one red per duplicate)
       StageScope st(ST_SCAN, stream, 1);
-      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, g.counters,
+      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, tile_order_out(img), g.counters,
                                                 speculate ? cap : 0xFFFFFFFFu, speculate ? lpad : 0xFFFFFFFFu,
                                                 cnt_stride(), true);
       GSR_LAUNCH_OK(debug, stream);
@@ -641,7 +679,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
           }
           // estimate too small: reset the scatter cursors (the scan rewrites them) and fall through
           StageScope st(ST_SCAN, stream, 1);
-          scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
+          scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, tile_order_out(img),
                                                     g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), true);
           GSR_LAUNCH_OK(debug, stream);
         }

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Turn the raw outputs of tools/gpu_final.sh (gpurun_out/final/) into the committed evidence under
+"""Turn the raw outputs of tools/gpu_r2_final.sh (gpurun_out/final2/) into the committed evidence under
 profiles/: bench lines, summarised ncu launch lists (per kernel: launches, mean time, share of the
 frame), ncu --set full summaries (tools/ncu_summary.py) and the DRAM-traffic table bench.py reads.
-Usage: python tools/collect_profiles.py <tag>      e.g. v5"""
+Usage: python tools/collect_profiles.py <tag>      e.g. v2   (after tools/gpu_r2_final.sh)"""
 import collections
 import csv
 import io
@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "gpurun_out", "final")
+SRC = os.path.join(ROOT, "gpurun_out", "final2")
 DST = os.path.join(ROOT, "profiles")
 
 
@@ -41,25 +41,24 @@ def launch_summary(path, out, title):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "vX"
     cp = lambda a, b: shutil.copy(os.path.join(SRC, a), os.path.join(DST, b))
-    cp("bench.json", "r01_bench_b200_C3_full_%s.json" % tag)
-    cp("bench_light.json", "r01_bench_b200_C3_light_%s.json" % tag)
-    cp("bench_ref.json", "r01_bench_reference_C3_full_%s.json" % tag)
-    cp("tracking_C2.jsonl", "r01_tracking_C2_%s.jsonl" % tag)
-    cp("configs.txt", "r01_configs_%s.txt" % tag)
-    launch_summary(os.path.join(SRC, "launches_C3.csv"), os.path.join(DST, "r01_ncu_launches_C3_full_%s.txt" % tag),
+    cp("bench.json", "r02_bench_b200_C3_full_%s.json" % tag)
+    cp("bench_light.json", "r02_bench_b200_C3_light_%s.json" % tag)
+    cp("bench_ref.json", "r02_bench_reference_C3_full_%s.json" % tag)
+    cp("tracking_C2.jsonl", "r02_tracking_C2_%s.jsonl" % tag)
+    cp("configs.txt", "r02_configs_%s.txt" % tag)
+    launch_summary(os.path.join(SRC, "launches_C3.csv"), os.path.join(DST, "r02_ncu_launches_C3_full_%s.txt" % tag),
                    "python bench.py --steps 2 --warmup 3 --cpu-frames 0   (C3 full; includes torch's own kernels)")
-    launch_summary(os.path.join(SRC, "launches_C4.csv"), os.path.join(DST, "r01_ncu_launches_C4_full_%s.txt" % tag),
+    launch_summary(os.path.join(SRC, "launches_C4.csv"), os.path.join(DST, "r02_ncu_launches_C4_full_%s.txt" % tag),
                    "python bench.py --config C4 --steps 2 --warmup 3 --cpu-frames 0   (C4 full)")
-    launch_summary(os.path.join(SRC, "tracking_launches.csv"), os.path.join(DST, "r01_ncu_launches_tracking_C2_%s.txt" % tag),
+    launch_summary(os.path.join(SRC, "tracking_launches.csv"), os.path.join(DST, "r02_ncu_launches_tracking_C2_%s.txt" % tag),
                    "python tools/bench_tracking.py --arms tracker --iters 6 --reps 1 under ncu --graph-profiling node")
     for cfg in ("C3", "C4"):
         raw = os.path.join(SRC, "prof_%s_raw.csv" % cfg)
         src = os.path.join(SRC, "prof_%s_src.csv" % cfg)
         args = [sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), raw] + ([src] if os.path.exists(src) else [])
         txt = subprocess.run(args, capture_output=True, text=True).stdout
-        with open(os.path.join(DST, "r01_ncu_full_%s_%s.txt" % (cfg, tag)), "w") as f:
-            f.write("# ncu --set full --clock-control none, one frame of bench.py --config %s (full variant): "
-                    "preprocess_fwd, render_fwd, render_bwd, preprocess_bwd\n" % cfg)
+        with open(os.path.join(DST, "r02_ncu_full_%s_%s.txt" % (cfg, tag)), "w") as f:
+            f.write("# ncu --set full --clock-control none, one frame of bench.py --config %s (full variant)\n" % cfg)
             f.write(txt)
     # DRAM traffic per launch of the blend kernels (bench.py: roofline.traffic)
     traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full "
@@ -81,7 +80,23 @@ def main():
             traffic.setdefault(key, {})[cfg] = int(tot)
             traffic.setdefault("inst_executed", {}).setdefault(key, {})[cfg] = int(float(d["smsp__inst_executed.sum"]))
     json.dump(traffic, open(os.path.join(DST, "ncu_traffic.json"), "w"), indent=1)
-    print(open(os.path.join(DST, "r01_ncu_launches_C3_full_%s.txt" % tag)).read())
+    # GPU test summary and sanitizer summaries
+    with open(os.path.join(DST, "r02_gputest_%s.txt" % tag), "w") as f:
+        f.write("# python -m pytest tests -m gpu -q   (B200, tools/gpu_r2_final.sh)\n")
+        f.write("".join(open(os.path.join(SRC, "pytest_gpu.log"), errors="replace").readlines()[-6:]))
+        f.write("\n# python -c 'import __graft_entry__ as g; g.smoke()'\n")
+        f.write("".join(open(os.path.join(SRC, "smoke.log"), errors="replace").readlines()[-6:]))
+    with open(os.path.join(DST, "r02_sanitizers_%s.txt" % tag), "w") as f:
+        f.write("# compute-sanitizer --tool <tool> python tools/sanitize_small.py  (both variants, every blend-kernel variant,\n"
+                "# radix + tile-local binning, a speculative frame that overflows and is redone, the exchange helpers, the loss\n"
+                "# helper, the tracker's CUDA graph); initcheck with bulk_sh=0 (it does not track cp.async.bulk global writes)\n")
+        for tool in ("memcheck", "racecheck", "initcheck"):
+            fn = os.path.join(SRC, "sanitize_%s.txt" % tool)
+            if os.path.exists(fn):
+                lines = open(fn, errors="replace").readlines()
+                keep = [l for l in lines if "ERROR SUMMARY" in l or "RACECHECK SUMMARY" in l or l.startswith("exit ") or "done" in l]
+                f.write("== %s ==\n%s" % (tool, "".join(keep[-8:])))
+    print(open(os.path.join(DST, "r02_ncu_launches_C3_full_%s.txt" % tag)).read())
     print(json.dumps(traffic, indent=1))
 
 
