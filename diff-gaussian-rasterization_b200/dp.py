@@ -107,9 +107,12 @@ class SceneGradReducer:
         self.stream = torch.cuda.Stream(device=device, priority=-1) if self.is_cuda else None
         self._work, self._done, self._attached = None, None, None
         import os
-        # the early gather pays from 4 ranks on (the gathered volume grows with the rank count; measured equal at 2)
+        # Early gather (the masked colour gradients leave the backward before its per-Gaussian kernel and are
+        # gathered by a P2P copy kernel underneath it): built and measured — equal at 2 ranks, 12 % / 30 % SLOWER at
+        # 4 / 8 (profiles/r02_scale_early_gather.txt: a copy kernel small enough not to disturb the per-Gaussian
+        # kernel is latency-bound on NVLink, and one more barrier is paid).  Off unless GSR_DP_EARLY_MIN_WORLD is set.
         self._early, self._no_early = False, bool(os.environ.get("GSR_DP_NO_EARLY"))
-        self._early_min_world = int(os.environ.get("GSR_DP_EARLY_MIN_WORLD", "4"))
+        self._early_min_world = int(os.environ.get("GSR_DP_EARLY_MIN_WORLD", str(1 << 30)))
         self._gather_blocks = int(os.environ.get("GSR_DP_GATHER_BLOCKS", "74"))
         self.slices = OrderedDict()
         num = lambda shape: int(torch.Size(shape).numel())
