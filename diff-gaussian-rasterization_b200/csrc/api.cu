@@ -24,7 +24,7 @@ std::atomic<long long> g_launches{0};
 // when it starts (OptionsCall), and everything below reads the snapshot: a concurrent
 // gsr_set_option from another thread can never change the switches in the middle of a call, and a
 // value one thread's call is using is never written by another thread.
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1, /*tile_lpt=*/0};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1, /*tile_lpt=*/0, /*early_acc_clear=*/1};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -190,6 +190,15 @@ Camera make_camera(const float* view, const float* proj, const float* campos, fl
   return c;
 }
 
+// The accumulator clear of the coming backward is forked off right in front of the forward blend kernel: the
+// memset then runs underneath that kernel (issue-bound, HBM idle) instead of next to the HBM-bound per-Gaussian
+// kernel, where it gained nothing (measured).  The geometry buffer's base address is the key the backward looks up.
+void begin_acc_clear_once(bool& begun, const GeomState& g, int P, cudaStream_t s) {
+  if (begun || options().early_acc_clear == 0) return;
+  begun = true;
+  acc_clear_begin(g.rec, g.acc, ((size_t)P * kAccStride + 16) * sizeof(float), s);
+}
+
 // shared front half of both forwards: allocate state, preprocess, bin
 int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinState& b,
                   ImgState& img, int* num_rendered, SpecRender* spec = nullptr) {
@@ -320,6 +329,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "fwd_packed")) return &g_opts.fwd_packed;
   if (!strcmp(key, "spec_render")) return &g_opts.spec_render;
   if (!strcmp(key, "tile_lpt")) return &g_opts.tile_lpt;
+  if (!strcmp(key, "early_acc_clear")) return &g_opts.early_acc_clear;
   return nullptr;
 }
 
@@ -396,7 +406,9 @@ int gsr_light_forward(
             tan_fovy, prefiltered, gt_depth, radii, debug, s, gau_uncertainty, gau_related_pixels};
   Camera cam; GeomState g; BinState b; ImgState img;
   SpecRender spec;
+  bool acc_begun = false;
   spec.launch = [&](const BinState& bs) {
+    begin_acc_clear_once(acc_begun, g, P, s);
     return launch_render_fwd_light(cam, g, bs, img, background, gt_depth, out_color, out_depth, out_median_depth,
                                    out_alpha, out_depth_var, gau_uncertainty, gau_related_pixels, debug != 0, s);
   };
@@ -449,7 +461,9 @@ int gsr_full_forward(
   Camera cam; GeomState g; BinState b; ImgState img;
   const bool count = options().exact_ng != 0;
   SpecRender spec;
+  bool acc_begun = false;
   spec.launch = [&](const BinState& bs) {
+    begin_acc_clear_once(acc_begun, g, P, s);
     return launch_render_fwd_full(cam, g, bs, img, background, out_color, out_depth, out_uncertainty, count, false, s);
   };
   spec.reset = []() { return (int)GSR_OK; };   // num_related is reset by the rescan of the redone binning
@@ -506,7 +520,11 @@ int gsr_light_backward(
   float* acc = scratch;
   unsigned int* done_counter = reinterpret_cast<unsigned int*>(scratch + (size_t)P * kAccStride);
   float* partials = scratch + (size_t)P * kAccStride + 16;
-  {
+  if (options().early_acc_clear != 0 && acc_clear_join(g.rec, s)) {
+    // cleared by the forward on a side stream (GeomState::acc): no memset in front of the blend kernel
+    acc = g.acc;
+    done_counter = reinterpret_cast<unsigned int*>(g.acc + (size_t)P * kAccStride);
+  } else {
     StageScope st(ST_MEMSET, s);
     GSR_CUDA_OK(cudaMemsetAsync(acc, 0, ((size_t)P * kAccStride + 16) * sizeof(float), s));
   }
@@ -562,7 +580,11 @@ int gsr_full_backward(
   float* acc = scratch;
   unsigned int* done_counter = reinterpret_cast<unsigned int*>(scratch + (size_t)P * kAccStride);
   float* partials = scratch + (size_t)P * kAccStride + 16;
-  {
+  if (options().early_acc_clear != 0 && acc_clear_join(g.rec, s)) {
+    // cleared by the forward on a side stream (GeomState::acc): no memset in front of the blend kernel
+    acc = g.acc;
+    done_counter = reinterpret_cast<unsigned int*>(g.acc + (size_t)P * kAccStride);
+  } else {
     StageScope st(ST_MEMSET, s);
     GSR_CUDA_OK(cudaMemsetAsync(acc, 0, ((size_t)P * kAccStride + 16) * sizeof(float), s));
   }

@@ -42,6 +42,7 @@ size_t GeomState::carve(GeomState& s, char* base, int P, size_t scan_bytes) {
   s.rect = c.take<uint2>((size_t)P);
   s.offsets = c.take<uint32_t>((size_t)P);
   s.counters = c.take<uint32_t>(8);
+  s.acc = c.take<float>((size_t)P * kAccStride + 16);   // before scan_temp: the backward re-derives with scan_bytes = 0
   s.scan_temp = c.take<char>(scan_bytes);
   s.scan_bytes = scan_bytes;
   return c.used + 256;
@@ -493,6 +494,38 @@ DeviceSlots* device_slots(int* device_out = nullptr) {
   return g_dev_slots[dev];
 }
 
+// ---- accumulator clear on a side stream (see gsr_common.cuh) -------------------------------------------------
+struct AccClear {
+  static constexpr int kRing = 16;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[kRing], done[kRing];
+  const void* key[kRing];
+  bool pending[kRing];
+  unsigned next = 0;
+  bool ok = false;
+  void init() {
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int i = 0; i < kRing; ++i) {
+      key[i] = nullptr; pending[i] = false;
+      if (cudaEventCreateWithFlags(&fork[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    }
+    ok = true;
+  }
+};
+AccClear* g_acc_clear[kMaxDevices] = {nullptr};
+
+AccClear* acc_clear_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (dev < 0 || dev >= kMaxDevices) return nullptr;
+  if (g_acc_clear[dev] == nullptr) {   // (caller holds g_ctx_mu)
+    g_acc_clear[dev] = new AccClear();   // leaked on purpose (outlives static destruction)
+    g_acc_clear[dev]->init();
+  }
+  return g_acc_clear[dev]->ok ? g_acc_clear[dev] : nullptr;
+}
+
 // Speculative-binning size estimate, one per (device, width, height, P) context: the sizes seen on
 // that context's previous frame size this frame's binning buffer before the count is known.  A
 // context speculates only while its estimate is `stable` (the last frame's counts would have fitted
@@ -586,6 +619,40 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
 // Sync-free binning into a caller-owned buffer of `capacity` entries whose longest tile list may
 // not exceed `longest_cap` (tracker: sizes come from a probing frame plus head room).  Nothing is
 // read back; overflow raises g.counters[3] and truncates the frame's lists (memory-safe).
+void acc_clear_begin(const void* geom_key, void* acc, size_t bytes, cudaStream_t stream) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  AccClear* a = acc_clear_state();
+  if (a == nullptr) return;
+  int i = -1;
+  for (int k = 0; k < AccClear::kRing; ++k)
+    if (a->key[k] == geom_key) i = k;            // the same buffer again: its old entry is stale
+  if (i < 0) i = (int)(a->next++ % AccClear::kRing);
+  a->key[i] = nullptr; a->pending[i] = false;
+  if (cudaEventRecord(a->fork[i], stream) != cudaSuccess || cudaStreamWaitEvent(a->side, a->fork[i], 0) != cudaSuccess ||
+      cudaMemsetAsync(acc, 0, bytes, a->side) != cudaSuccess || cudaEventRecord(a->done[i], a->side) != cudaSuccess) {
+    cudaGetLastError();   // the backward clears its own scratch
+    return;
+  }
+  a->key[i] = geom_key; a->pending[i] = true;
+}
+
+bool acc_clear_join(const void* geom_key, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  AccClear* a = acc_clear_state();
+  if (a == nullptr) return false;
+  for (int k = 0; k < AccClear::kRing; ++k) {
+    if (a->key[k] == geom_key && a->pending[k]) {
+      a->pending[k] = false;   // one backward per clear
+      a->key[k] = nullptr;
+      if (cudaStreamWaitEvent(stream, a->done[k], 0) != cudaSuccess) { cudaGetLastError(); return false; }
+      return true;
+    }
+  }
+  return false;
+}
+
 int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgState& img,
                        uint32_t capacity, uint32_t longest_cap, cudaStream_t stream) {
   const int tiles = cam.grid_x * cam.grid_y;

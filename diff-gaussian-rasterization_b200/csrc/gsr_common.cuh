@@ -57,6 +57,7 @@ struct Options {
   int fwd_packed;
   int spec_render;   // 1: forward blend enqueued before the host waits for the duplicate count
   int tile_lpt;      // 1: blend kernels take the tiles longest list first (ImgState::tile_order)
+  int early_acc_clear;  // 1: the forward clears the backward's accumulator on a side stream (acc_clear_begin)
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the
@@ -145,6 +146,9 @@ struct GeomState {
   uint2* rect;             // [P] tile rectangle: x = xmin | xmax << 16, y = ymin | ymax << 16
   uint32_t* offsets;       // [P] inclusive scan of tiles_touched
   uint32_t* counters;      // [8]  0: num_rendered, 1: num_related
+  float* acc;              // [16P + 16] the backward's accumulator lines + its last-block counter line, cleared by
+                           //            the FORWARD on a side stream (acc_clear_begin) so that the backward finds
+                           //            them zeroed instead of issuing a memset in front of its blend kernel
   char* scan_temp;
   size_t scan_bytes;
   static size_t carve(GeomState& s, char* base, int P, size_t scan_bytes);
@@ -173,6 +177,14 @@ struct ImgState {
                             //         (written by scan_tiles_kernel; 0xFFFFFFFF in [0] = identity)
   static size_t carve(ImgState& s, char* base, int HW, int tiles, int variant);
 };
+// Accumulator clear moved out of the backward's critical path: the forward enqueues the memset of GeomState::acc on
+// a library-owned side stream (ordered after everything already on `stream`, i.e. after the previous frame), where
+// it runs underneath the forward's kernels; the backward of the same geometry buffer makes its stream wait for it
+// (acc_clear_join returns true) or, if nothing is pending for that buffer (second backward of one forward, ring
+// overrun, option off), clears its scratch itself as before.
+void acc_clear_begin(const void* geom_key, void* acc, size_t bytes, cudaStream_t stream);
+bool acc_clear_join(const void* geom_key, cudaStream_t stream);
+
 // the tile order handed to the blend kernels (NULL = CTA i takes tile i)
 inline const uint32_t* tile_order_arg(const ImgState& img) { return options().tile_lpt != 0 ? img.tile_order : nullptr; }
 

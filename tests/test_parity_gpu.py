@@ -523,6 +523,65 @@ def test_unwanted_gradients_are_not_written(built):
             assert rel < 1e-4, k
 
 
+@pytest.mark.parametrize("variant", ["light", "full"])
+def test_accumulator_cleared_by_the_forward_on_a_side_stream(built, variant):
+    """early_acc_clear: the forward clears the backward's accumulator (inside the geometry buffer) on a side
+    stream; the backward of that buffer waits for it instead of issuing a memset.  Same gradients as with the
+    memset; two forwards before their two backwards (in the other order) each find their own cleared
+    accumulator; a second backward of ONE forward (retain_graph) finds nothing pending and clears its own."""
+    sc = ge.load_scene_module()
+    mod = built.load_variant(variant)
+    cam_a, cam_b = sc.make_camera(200, 136, seed=0), sc.make_camera(200, 136, seed=1)
+    scene = sc.make_scene(8000, cam_a, (1.0, 8.0), seed=33)
+    cot = sc.make_cotangents(cam_a, _n_aux(variant))
+    pu.set_option("early_acc_clear", 0)
+    try:
+        ref = {c: pu.run_variant(mod, variant, c, scene, cot)[1] for c in (cam_a, cam_b)}
+    finally:
+        pu.set_option("early_acc_clear", 1)
+
+    def same(g, r):
+        for k in r:
+            rel, _ = pu.grad_mismatch(g[k], r[k], rtol=1e-4)
+            assert rel < 1e-4, k
+    for c in (cam_a, cam_b):
+        same(pu.run_variant(mod, variant, c, scene, cot)[1], ref[c])
+
+    # two forwards, then the two backwards in the other order; then a second backward of the first forward
+    d = lambda t: t.to(DEV).clone().requires_grad_(True)
+    params = dict(means3D=d(scene.means3D), opacities=d(scene.opacities), shs=d(scene.shs), scales=d(scene.scales),
+                  rotations=d(scene.rotations))
+    ccol, caux = cot
+
+    def forward(cam):
+        view = d(cam.viewmatrix)
+        rast = mod.GaussianRasterizer(pu.settings_for(mod, variant, cam, scene, DEV, 3, False, False))
+        res = rast(means2D=torch.zeros_like(params["means3D"], requires_grad=True), viewmatrix=view,
+                   gt_depth=scene.gt_depth.to(DEV), **params)
+        if variant == "light":
+            loss = ((res[0] * ccol.to(DEV)).sum() + (res[2] * caux[0].to(DEV)).sum() + (res[3] * caux[1].to(DEV)).sum() +
+                    (res[4] * caux[2].to(DEV)).sum())
+        else:
+            loss = (res[0] * ccol.to(DEV)).sum() + (res[2] * caux[0].to(DEV)).sum() + (res[3] * caux[1].to(DEV)).sum()
+        return loss, view
+
+    def grads_of(loss, view, retain=False):
+        for t in params.values():
+            t.grad = None
+        view.grad = None
+        loss.backward(retain_graph=retain)
+        g = {k: v.grad.detach().cpu().numpy() for k, v in params.items()}
+        g["viewmatrix"] = view.grad.detach().cpu().numpy()
+        return g
+    la, va = forward(cam_a)
+    lb, vb = forward(cam_b)
+    gb = grads_of(lb, vb)
+    ga = grads_of(la, va, retain=True)
+    ga2 = grads_of(la, va)
+    for g, r in ((ga, ref[cam_a]), (gb, ref[cam_b]), (ga2, ref[cam_a])):
+        same(g, {k: r[k] for k in g})
+
+
 def test_two_rasterizers_interleaved_on_two_streams(built):
     """Library state is per (device, image size, Gaussian count) context: a 640x480 -light tracker-size
     rasterizer and a 1080p-ish -full one, interleaved frame by frame on two streams of one process, give
