@@ -20,7 +20,12 @@ namespace {
 
 char* resize_cb(void* ctx, size_t bytes) {
   auto* t = static_cast<torch::Tensor*>(ctx);
-  t->resize_({static_cast<long long>(bytes)});
+  // growing a buffer that already holds something (the binning buffer after a speculation miss): resize_ would
+  // copy the old contents into the new storage; a fresh tensor does not (the old storage is released in stream order)
+  if (t->numel() != 0 && static_cast<size_t>(t->numel()) < bytes)
+    *t = torch::empty({static_cast<long long>(bytes)}, t->options());
+  else
+    t->resize_({static_cast<long long>(bytes)});
   return reinterpret_cast<char*>(t->data_ptr());
 }
 

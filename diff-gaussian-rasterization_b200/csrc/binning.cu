@@ -426,7 +426,8 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, const uint64_t* _
   for (int i = tid; i < n; i += kTileSortThreads) out[i] = (uint32_t)s[i];
 }
 
-__global__ void __launch_bounds__(kTileSortThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kTileSortThreads, MINB)
 sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
                   uint32_t* __restrict__ vals, uint32_t capacity, int smem_entries) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
@@ -603,12 +604,17 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
     // the opt-in to > 48 KB of dynamic shared memory is per device (and only needed for long lists)
     DeviceSlots* ds = smem > 48 * 1024 ? device_slots() : nullptr;
     if (smem > 48 * 1024 && (ds == nullptr || !ds->sort_attr_set)) {
-      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kTileSortCap * (int)sizeof(uint64_t)));
+      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kTileSortCap * (int)sizeof(uint64_t)));
       if (ds != nullptr) ds->sort_attr_set = true;
     }
-    sort_tiles_kernel<<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals,
-                                                                capacity, p);
+    // "pre_occ" = 1 (A/B): the 64-register build, 4 CTAs per SM instead of 3
+    if (options().pre_occ == 1)
+      sort_tiles_kernel<4><<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals, capacity, p);
+    else
+      sort_tiles_kernel<1><<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals, capacity, p);
     GSR_LAUNCH_OK(debug, stream);
   }
   return GSR_OK;

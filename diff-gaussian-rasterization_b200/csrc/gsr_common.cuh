@@ -58,6 +58,7 @@ struct Options {
   int spec_render;   // 1: forward blend enqueued before the host waits for the duplicate count
   int tile_lpt;      // 1: blend kernels take the tiles longest list first (ImgState::tile_order)
   int early_acc_clear;  // 1: the forward clears the backward's accumulator on a side stream (acc_clear_begin)
+  int pre_occ;          // A/B: 1 = per-Gaussian kernels built for 8 (forward) / 6 (backward) CTAs per SM
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the

@@ -63,7 +63,7 @@ def main():
     # DRAM traffic per launch of the blend kernels (bench.py: roofline.traffic)
     traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full "
                "--clock-control none` captures under gpurun (bytes); read by bench.py for roofline.traffic. "
-               "Source: profiles/r01_ncu_full_C3_%s.txt / r01_ncu_full_C4_%s.txt" % (tag, tag)}
+               "Source: profiles/r02_ncu_full_C3_%s.txt / r02_ncu_full_C4_%s.txt" % (tag, tag)}
     for cfg in ("C3", "C4"):
         rows = list(csv.reader(open(os.path.join(SRC, "prof_%s_raw.csv" % cfg))))
         hdr, units = rows[0], rows[1]
