@@ -24,7 +24,7 @@ std::atomic<long long> g_launches{0};
 // when it starts (OptionsCall), and everything below reads the snapshot: a concurrent
 // gsr_set_option from another thread can never change the switches in the middle of a call, and a
 // value one thread's call is using is never written by another thread.
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1, /*tile_lpt=*/0, /*early_acc_clear=*/1, /*pre_occ=*/0};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1, /*early_acc_clear=*/1};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -225,10 +225,8 @@ int forward_front(const FwdArgs& a, int variant, Camera& cam, GeomState& g, BinS
     StageScope st(ST_MEMSET, a.stream, 1);
     if (tile_local)
       GSR_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * (size_t)tiles * cnt_stride(), a.stream));
-    else {
+    else
       GSR_CUDA_OK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), a.stream));
-      GSR_CUDA_OK(cudaMemsetAsync(img.tile_order, 0xFF, sizeof(uint32_t), a.stream));   // identity (no tile scan here)
-    }
   }
   int rc = launch_preprocess_fwd(a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations,
                                  a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, cam,
@@ -328,9 +326,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "bwd_occ")) return &g_opts.bwd_occ;
   if (!strcmp(key, "fwd_packed")) return &g_opts.fwd_packed;
   if (!strcmp(key, "spec_render")) return &g_opts.spec_render;
-  if (!strcmp(key, "tile_lpt")) return &g_opts.tile_lpt;
   if (!strcmp(key, "early_acc_clear")) return &g_opts.early_acc_clear;
-  if (!strcmp(key, "pre_occ")) return &g_opts.pre_occ;
   return nullptr;
 }
 

@@ -65,7 +65,6 @@ size_t ImgState::carve(ImgState& s, char* base, int HW, int tiles, int variant) 
   s.tile_last = c.take<uint32_t>((size_t)tiles);
   s.tile_count = c.take<uint32_t>((size_t)tiles * kCntStrideMax);
   s.tile_fill = c.take<uint32_t>((size_t)tiles * kCntStrideMax);
-  s.tile_order = c.take<uint32_t>((size_t)tiles);
   s.n_contrib = c.take<uint32_t>((size_t)HW);
   if (variant == kFull) {
     s.final_T = c.take<float>((size_t)HW);
@@ -78,9 +77,6 @@ size_t ImgState::carve(ImgState& s, char* base, int HW, int tiles, int variant) 
 }
 
 namespace {
-
-// tile_order is only produced when the blend kernels use it (option tile_lpt)
-inline uint32_t* tile_order_out(const ImgState& img) { return options().tile_lpt != 0 ? img.tile_order : nullptr; }
 
 // smallest b with (n >> b) == 0, i.e. the number of bits needed for tile ids < n
 // (same value the reference's getHigherMsb produces)
@@ -157,24 +153,14 @@ constexpr int kTileSortThreads = 256;
 // starts go back through shared memory to coalesced stores — 4 barriers per 8192 tiles.
 // reset_counters: this kernel is the first writer of the frame's counter block and initialises all of
 // it (no memset pass); the tracker passes false, its overflow flag is sticky across iterations.
-// tile_order: the tiles sorted by descending list length (counting sort over kOrderBins length classes of 16
-// entries; order inside a class is arbitrary): the blend kernels' CTA i takes tile tile_order[i], so the long
-// tiles start first and the short ones fill the tail of the kernel (gsr_common.cuh: tile_of_block).
 constexpr int kScanPer = 8;
-constexpr int kOrderBins = 256;
-__device__ __forceinline__ int order_bin(uint32_t count) {
-  const uint32_t c = count >> 4;
-  return (kOrderBins - 1) - (int)(c < (uint32_t)(kOrderBins - 1) ? c : (uint32_t)(kOrderBins - 1));
-}
 __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ tile_order,
-                  uint32_t* __restrict__ counters,
+                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ counters,
                   uint32_t capacity, uint32_t longest_cap, int cs, bool reset_counters) {
   __shared__ uint32_t s_cnt[1024 * (kScanPer + 1)];   // one pad word per 8: the stride-8 reads become stride 9
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry, s_max;
-  __shared__ uint32_t s_bin[kOrderBins];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto slot = [](int i) { return i + (i >> 3); };
   if (tid == 0) { s_carry = 0; s_max = 0; }
@@ -239,30 +225,6 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
   for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
   if (lane == 0) atomicMax(&s_max, local_max);
   __syncthreads();
-  if (tile_order != nullptr) {
-    // counting sort of the tiles by length class (the counts are L2-hot: this kernel just read them)
-    for (int b = tid; b < kOrderBins; b += 1024) s_bin[b] = 0u;
-    __syncthreads();
-    for (int t = tid; t < tiles; t += 1024) atomicAdd(&s_bin[order_bin(tile_count[(size_t)t * cs])], 1u);
-    __syncthreads();
-    if (warp == 0) {   // exclusive scan of the 256 class sizes: 8 per lane
-      uint32_t v8[kOrderBins / 32], sum8 = 0;
-#pragma unroll
-      for (int k = 0; k < kOrderBins / 32; ++k) { v8[k] = s_bin[lane * (kOrderBins / 32) + k]; sum8 += v8[k]; }
-      uint32_t inc8 = sum8;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, inc8, o);
-        if (lane >= o) inc8 += n;
-      }
-      uint32_t start8 = inc8 - sum8;
-#pragma unroll
-      for (int k = 0; k < kOrderBins / 32; ++k) { s_bin[lane * (kOrderBins / 32) + k] = start8; start8 += v8[k]; }
-    }
-    __syncthreads();
-    for (int t = tid; t < tiles; t += 1024)
-      tile_order[atomicAdd(&s_bin[order_bin(tile_count[(size_t)t * cs])], 1u)] = (uint32_t)t;
-  }
   if (tid == 0) {
     const bool cut = s_carry > capacity || s_max > longest_cap;
     counters[0] = s_carry;
@@ -426,8 +388,9 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, const uint64_t* _
   for (int i = tid; i < n; i += kTileSortThreads) out[i] = (uint32_t)s[i];
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(kTileSortThreads, MINB)
+// built for 4 CTAs per SM (64 registers, no spills): 0.047 ms at C3 against 0.053 with the compiler's own choice of
+// 80 registers / 3 CTAs (profiles/r02_ab_pre_occ.txt)
+__global__ void __launch_bounds__(kTileSortThreads, 4)
 sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
                   uint32_t* __restrict__ vals, uint32_t capacity, int smem_entries) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
@@ -604,17 +567,11 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
     // the opt-in to > 48 KB of dynamic shared memory is per device (and only needed for long lists)
     DeviceSlots* ds = smem > 48 * 1024 ? device_slots() : nullptr;
     if (smem > 48 * 1024 && (ds == nullptr || !ds->sort_attr_set)) {
-      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kTileSortCap * (int)sizeof(uint64_t)));
-      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      GSR_CUDA_OK(cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kTileSortCap * (int)sizeof(uint64_t)));
       if (ds != nullptr) ds->sort_attr_set = true;
     }
-    // "pre_occ" = 1 (A/B): the 64-register build, 4 CTAs per SM instead of 3
-    if (options().pre_occ == 1)
-      sort_tiles_kernel<4><<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals, capacity, p);
-    else
-      sort_tiles_kernel<1><<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals, capacity, p);
+    sort_tiles_kernel<<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals, capacity, p);
     GSR_LAUNCH_OK(debug, stream);
   }
   return GSR_OK;
@@ -665,7 +622,7 @@ int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgS
   if (longest_cap > (uint32_t)kTileSortCap) longest_cap = kTileSortCap;
   {
     StageScope st(ST_SCAN, stream, 1);
-    scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, tile_order_out(img),
+    scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
                                               g.counters, capacity, longest_cap, cnt_stride(), false);
     GSR_LAUNCH_OK(false, stream);
   }
@@ -676,7 +633,7 @@ int run_binning_static(int P, const Camera& cam, GeomState& g, BinState& b, ImgS
 // in g.counters[2] for the caller to read back.
 int probe_tile_counts(const Camera& cam, GeomState& g, ImgState& img, cudaStream_t stream) {
   scan_tiles_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges,
-                                            img.tile_fill, tile_order_out(img), g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), false);
+                                            img.tile_fill, g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), false);
   GSR_LAUNCH_OK(false, stream);
   return GSR_OK;
 }
@@ -715,7 +672,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     {
       // img.tile_count was filled by preprocess_fwd (one red per duplicate)
       StageScope st(ST_SCAN, stream, 1);
-      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, tile_order_out(img), g.counters,
+      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, g.counters,
                                                 speculate ? cap : 0xFFFFFFFFu, speculate ? lpad : 0xFFFFFFFFu,
                                                 cnt_stride(), true);
       GSR_LAUNCH_OK(debug, stream);
@@ -752,7 +709,7 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
           }
           // estimate too small: reset the scatter cursors (the scan rewrites them) and fall through
           StageScope st(ST_SCAN, stream, 1);
-          scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, tile_order_out(img),
+          scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill,
                                                     g.counters, 0xFFFFFFFFu, 0xFFFFFFFFu, cnt_stride(), true);
           GSR_LAUNCH_OK(debug, stream);
         }

@@ -56,9 +56,7 @@ struct Options {
   int bwd_occ;
   int fwd_packed;
   int spec_render;   // 1: forward blend enqueued before the host waits for the duplicate count
-  int tile_lpt;      // 1: blend kernels take the tiles longest list first (ImgState::tile_order)
   int early_acc_clear;  // 1: the forward clears the backward's accumulator on a side stream (acc_clear_begin)
-  int pre_occ;          // A/B: 1 = per-Gaussian kernels built for 8 (forward) / 6 (backward) CTAs per SM
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the
@@ -174,8 +172,6 @@ struct ImgState {
   uint32_t* tile_last;      // [tiles] max n_contrib over the tile's pixels
   uint32_t* tile_count;     // [tiles] entries per tile (tile-local binning)
   uint32_t* tile_fill;      // [tiles] scatter cursor per tile
-  uint32_t* tile_order;     // [tiles] CTA i of the blend kernels takes tile tile_order[i]: longest lists first
-                            //         (written by scan_tiles_kernel; 0xFFFFFFFF in [0] = identity)
   static size_t carve(ImgState& s, char* base, int HW, int tiles, int variant);
 };
 // Accumulator clear moved out of the backward's critical path: the forward enqueues the memset of GeomState::acc on
@@ -185,9 +181,6 @@ struct ImgState {
 // overrun, option off), clears its scratch itself as before.
 void acc_clear_begin(const void* geom_key, void* acc, size_t bytes, cudaStream_t stream);
 bool acc_clear_join(const void* geom_key, cudaStream_t stream);
-
-// the tile order handed to the blend kernels (NULL = CTA i takes tile i)
-inline const uint32_t* tile_order_arg(const ImgState& img) { return options().tile_lpt != 0 ? img.tile_order : nullptr; }
 
 size_t scan_temp_bytes(int P);
 size_t sort_temp_bytes(size_t N, int end_bit);
@@ -347,19 +340,6 @@ __device__ __forceinline__ unsigned block_mask16(const float4& r0, const float4&
     if (y1 >= by && y0 <= by + 3.0f) mask |= col << (4 * r);
   }
   return mask;
-}
-
-// CTA -> tile of the blend kernels.  The hardware hands out CTAs in index order, so with the tiles sorted by
-// descending list length (scan_tiles_kernel) the long tiles start first and the short ones fill the tail
-// (longest-processing-time-first): no wave of a few long tiles running alone at the end of a kernel.
-struct TileOfBlock { int tile, bx, by; };
-__device__ __forceinline__ TileOfBlock tile_of_block(const uint32_t* __restrict__ tile_order, int block, int grid_x) {
-  TileOfBlock t;
-  t.tile = block;
-  if (tile_order != nullptr && tile_order[0] != 0xFFFFFFFFu) t.tile = (int)tile_order[block];
-  t.by = t.tile / grid_x;
-  t.bx = t.tile - t.by * grid_x;
-  return t;
 }
 
 // Pixel <-> thread mapping of the blend kernels: warp w covers the 8x4 block at column (w & 1),

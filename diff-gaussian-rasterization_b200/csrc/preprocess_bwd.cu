@@ -611,16 +611,8 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
       P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
       cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
       g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr, done_counter)
-#define GSR_PRE_BWD6(V)                                                                          \
-  prefer_max_shared_once(reinterpret_cast<const void*>(&preprocess_bwd_kernel<V, 16, true, 6>)); \
-  preprocess_bwd_kernel<V, 16, true, 6><<<blocks, kBwdThreads, smem, stream>>>(                  \
-      P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
-      cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
-      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr, done_counter)
 #define GSR_PRE_BWD_M(V)                                                                         \
-  if (tma && M == 16 && options().pre_occ == 1) {   /* A/B: 6 CTAs per SM (80 registers) */       \
-    GSR_PRE_BWD6(V);                                                                             \
-  } else if (tma) {                                                                              \
+  if (tma) {   /* 5 CTAs per SM (96 registers); the 6-CTA build (80 registers, 72 bytes spilled) measured equal */ \
     if (M == 16) { GSR_PRE_BWD(V, 16, true); } else { GSR_PRE_BWD(V, 4, true); }                 \
   } else {                                                                                       \
     switch (M) {                                                                                 \

@@ -177,8 +177,9 @@ constexpr int kMaxCoeffs = 16;
 // SH coefficients of a block of Gaussians are contiguous in memory ([P, M, 3] fp32): the block
 // streams its slab with coalesced 128-bit loads into shared memory (row stride M*3+1 floats to
 // spread banks) and each thread then reads its own row.
-template <int MT, bool TMA, int MINB = 7>  // MT: compile-time number of SH coefficients (16 / 9 / 4 / 1) or 0 = runtime M
-__global__ void __launch_bounds__(kPreThreads, MINB)
+// 7 CTAs per SM (72 registers); the 8-CTA build (64 registers, 24 bytes spilled) measured slower: 0.067 vs 0.064 ms at C3
+template <int MT, bool TMA>  // MT: compile-time number of SH coefficients (16 / 9 / 4 / 1) or 0 = runtime M
+__global__ void __launch_bounds__(kPreThreads, 7)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ scales, float scale_modifier,
                       const float* __restrict__ rotations, const float* __restrict__ opacities,
@@ -404,15 +405,7 @@ int launch_preprocess_fwd(int P, int D, int M, const float* means3D, const float
       cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,        \
       g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0,            \
       (uint32_t)cnt_stride(), zero_f32, zero_i32)
-  if (tma && M == 16 && options().pre_occ == 1) {   // A/B: 8 CTAs per SM (64 registers, 24 bytes spilled)
-    prefer_max_shared_once(reinterpret_cast<const void*>(&preprocess_fwd_kernel<16, true, 8>));
-    preprocess_fwd_kernel<16, true, 8><<<blocks, kPreThreads, smem, stream>>>(
-        P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
-        colors_precomp, cam.view, cam.proj, cam.campos, cam.W, cam.H, cam.tan_fovx, cam.tan_fovy,
-        cam.focal_x, cam.focal_y, cam.grid_x, cam.grid_y, radii, g.rec, g.cov3D, g.clamped,
-        g.tiles_touched, g.rect, tile_count, prefiltered, options().tight_tiles != 0,
-        (uint32_t)cnt_stride(), zero_f32, zero_i32);
-  } else if (tma) {
+  if (tma) {
     if (M == 16) { GSR_PRE_FWD(16, true); } else { GSR_PRE_FWD(4, true); }
   } else {
     switch (M) {

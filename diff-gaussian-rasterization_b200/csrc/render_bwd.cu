@@ -64,7 +64,7 @@ __device__ __forceinline__ float row16_sum(unsigned addr) {
 template <int VARIANT, bool POSE_ONLY>
 __global__ void __launch_bounds__(kTileThreads)
 render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                  const uint32_t* __restrict__ tile_last, int W, int H, int grid_x, const uint32_t* __restrict__ tile_order,
+                  const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
                   const float4* __restrict__ rec, const float* __restrict__ bg,
                   const float* __restrict__ gt_depth,
                   const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
@@ -83,13 +83,12 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const TileOfBlock tob = tile_of_block(tile_order, (int)blockIdx.x, grid_x);
-  const int tile = tob.tile;
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
   int lx, ly, sub;
   pixel_of_thread(warp, lane, lx, ly, sub);
   const int half = lane >> 4;
-  const int px = tob.bx * kTileX + lx;
-  const int py = tob.by * kTileY + ly;
+  const int px = blockIdx.x * kTileX + lx;
+  const int py = blockIdx.y * kTileY + ly;
   const bool inside = px < W && py < H;
   const uint32_t pix_id = (uint32_t)W * (uint32_t)py + (uint32_t)px;
   const float pixfx = (float)px, pixfy = (float)py;
@@ -124,7 +123,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   bool mid_once = true;
   const unsigned red_st = smem_u32(&s_red[0][tid]);
   const unsigned red_ld = smem_u32(&s_red[(lane >> 1) % kRedVals][(tid & ~31) + (lane & 1) * 16]);
-  const float tile_x0 = (float)(tob.bx * kTileX), tile_y0 = (float)(tob.by * kTileY);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
 
   for (int i = 0; i < rounds; ++i) {
     __syncthreads();
@@ -308,7 +307,7 @@ __device__ __forceinline__ unsigned block_mask4(const float4& r0, const float4& 
 template <int VARIANT, bool POSE_ONLY>
 __global__ void __launch_bounds__(kBwd2Threads, 8)
 render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x, const uint32_t* __restrict__ tile_order,
+                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
                    const float4* __restrict__ rec, const float* __restrict__ bg,
                    const float* __restrict__ gt_depth,
                    const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
@@ -329,17 +328,16 @@ render_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const TileOfBlock tob = tile_of_block(tile_order, (int)blockIdx.x, grid_x);
-  const int tile = tob.tile;
-  const int px = tob.bx * kTileX + (warp & 1) * 8 + (lane & 7);
-  const int py0 = tob.by * kTileY + (warp >> 1) * 8 + 2 * (lane >> 3);
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
+  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (lane & 7);
+  const int py0 = blockIdx.y * kTileY + (warp >> 1) * 8 + 2 * (lane >> 3);
   const int py1 = py0 + 1;
   const bool in_a = px < W && py0 < H, in_b = px < W && py1 < H;
   const uint32_t pix_a = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
   const uint32_t pix_b = pix_a + (uint32_t)W;
   const float pxf = (float)px;
   const f2 npy2 = f2_pack(-(float)py0, -(float)py1);
-  const float tile_x0 = (float)(tob.bx * kTileX), tile_y0 = (float)(tob.by * kTileY);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
 
   const uint2 range = ranges[tile];
   const int walk = (int)tile_last[tile];  // entries [0, walk) were used by some pixel
@@ -558,7 +556,7 @@ __device__ __forceinline__ float row8_sum(unsigned addr) {
 template <int VARIANT, bool POSE_ONLY, int MINB>
 __global__ void __launch_bounds__(kBwdQThreads, MINB)
 render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x, const uint32_t* __restrict__ tile_order,
+                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
                    const float4* __restrict__ rec, const float* __restrict__ bg,
                    const float* __restrict__ gt_depth,
                    const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
@@ -584,18 +582,17 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   const int quarter = lane >> 3, ql = lane & 7;
   // lists start zeroed: slots beyond a quarter's length are read (and ignored) by its lanes
   reinterpret_cast<uint4*>(&s_list[0][0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);
-  const TileOfBlock tob = tile_of_block(tile_order, (int)blockIdx.x, grid_x);
-  const int tile = tob.tile;
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
   // warp -> 8x8 block (column warp & 1, row warp >> 1); quarter -> 4x4 block inside it; lane -> a 1x2 column
-  const int px = tob.bx * kTileX + (warp & 1) * 8 + (quarter & 1) * 4 + (ql & 3);
-  const int py0 = tob.by * kTileY + (warp >> 1) * 8 + (quarter >> 1) * 4 + 2 * (ql >> 2);
+  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (quarter & 1) * 4 + (ql & 3);
+  const int py0 = blockIdx.y * kTileY + (warp >> 1) * 8 + (quarter >> 1) * 4 + 2 * (ql >> 2);
   const int py1 = py0 + 1;
   const bool in_a = px < W && py0 < H, in_b = px < W && py1 < H;
   const uint32_t pix_a = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
   const uint32_t pix_b = pix_a + (uint32_t)W;
   const float pxf = (float)px;
   const f2 npy2 = f2_pack(-(float)py0, -(float)py1);
-  const float tile_x0 = (float)(tob.bx * kTileX), tile_y0 = (float)(tob.by * kTileY);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
   // bit of this warp's quarter 0 in block_mask16 (bit = 4 * block row + block column of the 4x4 blocks);
   // quarters 1, 2, 3 are bits +1, +4, +5
   const int sub0 = 4 * (2 * (warp >> 1)) + 2 * (warp & 1);
@@ -904,7 +901,7 @@ __device__ __forceinline__ float row4_sum(unsigned addr) {
 template <int VARIANT, bool POSE_ONLY>
 __global__ void __launch_bounds__(32, 16)
 render_bwdo_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x, const uint32_t* __restrict__ tile_order,
+                   const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
                    const float4* __restrict__ rec, const float* __restrict__ bg,
                    const float* __restrict__ gt_depth,
                    const float* __restrict__ alphas,      // light: T_final = 1 - alphas[pix]
@@ -925,16 +922,15 @@ render_bwdo_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   const int lane = threadIdx.x;
   const int e = lane >> 2, l = lane & 3;     // group (4x4 block) and column inside it
   reinterpret_cast<uint4*>(&s_list[0][0])[lane] = make_uint4(0u, 0u, 0u, 0u);   // 64 x 8 bytes = 32 x 16
-  const TileOfBlock tob = tile_of_block(tile_order, (int)blockIdx.x >> 1, grid_x);
-  const int tile_x = tob.bx, half = (int)blockIdx.x & 1;                        // half: rows 8 half .. 8 half + 7
-  const int tile = tob.tile;
+  const int tile_x = (int)blockIdx.x >> 1, half = (int)blockIdx.x & 1;          // half: rows 8 half .. 8 half + 7
+  const int tile = blockIdx.y * grid_x + tile_x;
   const int px = tile_x * kTileX + (e & 3) * 4 + l;
-  const int py0 = tob.by * kTileY + half * 8 + (e >> 2) * 4;
+  const int py0 = blockIdx.y * kTileY + half * 8 + (e >> 2) * 4;
   const bool in_x = px < W;
   const uint32_t pix0 = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
   const float pxf = (float)px;
   const f2 npyA = f2_pack(-(float)py0, -(float)(py0 + 1)), npyB = f2_pack(-(float)(py0 + 2), -(float)(py0 + 3));
-  const float tile_x0 = (float)(tile_x * kTileX), tile_y0 = (float)(tob.by * kTileY);
+  const float tile_x0 = (float)(tile_x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
 
   const uint2 range = ranges[tile];
   const int walk = (int)tile_last[tile];  // entries [0, walk) were used by some pixel
@@ -1115,7 +1111,7 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
                       const ImgState& img, const float* bg, const float* gt_depth,
                       const float* alphas, const BlendGrads& cot, float* acc, int num_gaussians,
                       int num_entries, bool pose_only, bool debug, cudaStream_t stream) {
-  dim3 grid(cam.grid_x * cam.grid_y, 1, 1);   // CTA -> tile through img.tile_order
+  dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_BWD, stream);
   // "bwd_packed": 0 scalar 8x4 kernel, 1 packed 8x8 kernel (one list per warp), 3 packed kernel with
   // quarter-warp lists, 2 (default) = 3.  "bwd_occ": CTAs per SM the quarter kernel is compiled for
@@ -1130,14 +1126,14 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
   const bool occ7 = options().bwd_occ != 8;
   (void)num_gaussians; (void)num_entries;
 #define GSR_BWD_ARGS(FT, FC)                                                                       \
-  img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, gt_depth, alphas, FT,    \
+  img.ranges, b.vals, img.tile_last, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, alphas, FT,    \
       img.n_contrib, FC, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar, acc
 #define GSR_BWDQ(V, PO, FT, FC)                                                                    \
   do {                                                                                             \
     if (occ7) render_bwdq_kernel<V, PO, 7><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC)); \
     else render_bwdq_kernel<V, PO, 8><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC));    \
   } while (0)
-  const dim3 grid_o(2 * cam.grid_x * cam.grid_y, 1, 1);   // octet kernel: one warp per half tile
+  const dim3 grid_o(2 * cam.grid_x, cam.grid_y, 1);   // octet kernel: one warp per half tile
   if (octet) {
     if (variant == kLight && pose_only)
       render_bwdo_kernel<kLight, true><<<grid_o, 32, 0, stream>>>(GSR_BWD_ARGS(nullptr, nullptr));

@@ -27,7 +27,7 @@ namespace {
 template <int VARIANT, bool LOSS>
 __global__ void __launch_bounds__(kTileThreads)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                  int W, int H, int grid_x, const uint32_t* __restrict__ tile_order, const float4* __restrict__ rec,
+                  int W, int H, int grid_x, const float4* __restrict__ rec,
                   const float* __restrict__ bg, const float* __restrict__ gt_depth,
                   float* __restrict__ out_color, float* __restrict__ out_depth,
                   float* __restrict__ out_aux0,   // light: alpha      full: uncertainty
@@ -46,13 +46,12 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const TileOfBlock tob = tile_of_block(tile_order, (int)blockIdx.x, grid_x);
-  const int tile = tob.tile;
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
   int lx, ly, sub;
   pixel_of_thread(warp, lane, lx, ly, sub);
   const int half = lane >> 4;
-  const int px = tob.bx * kTileX + lx;
-  const int py = tob.by * kTileY + ly;
+  const int px = blockIdx.x * kTileX + lx;
+  const int py = blockIdx.y * kTileY + ly;
   const bool inside = px < W && py < H;
   const uint32_t pix_id = (uint32_t)W * (uint32_t)py + (uint32_t)px;
   const float pixfx = (float)px, pixfy = (float)py;
@@ -65,7 +64,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   bool done = !inside;
   float T = 1.0f;
   uint32_t last_contributor = 0, first = 0xFFFFFFFFu, valid = 0;
-  const float tile_x0 = (float)(tob.bx * kTileX), tile_y0 = (float)(tob.by * kTileY);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, Wsum = 0.f, Dmed = 0.f;
   float gt = 0.f;
   if (VARIANT == kLight && inside) gt = gt_depth[pix_id];
@@ -256,7 +255,7 @@ constexpr int kFwdQBatch = 128;
 template <int VARIANT, bool LOSS, bool COUNT>
 __global__ void __launch_bounds__(kFwdQThreads, 8)
 render_fwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                   int W, int H, int grid_x, const uint32_t* __restrict__ tile_order, const float4* __restrict__ rec,
+                   int W, int H, int grid_x, const float4* __restrict__ rec,
                    const float* __restrict__ bg, const float* __restrict__ gt_depth,
                    float* __restrict__ out_color, float* __restrict__ out_depth,
                    float* __restrict__ out_aux0,   // light: alpha      full: uncertainty
@@ -276,18 +275,17 @@ render_fwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int quarter = lane >> 3, ql = lane & 7;
-  const TileOfBlock tob = tile_of_block(tile_order, (int)blockIdx.x, grid_x);
-  const int tile = tob.tile;
+  const int tile = blockIdx.y * grid_x + blockIdx.x;
   reinterpret_cast<uint4*>(&s_list[0][0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);
-  const int px = tob.bx * kTileX + (warp & 1) * 8 + (quarter & 1) * 4 + (ql & 3);
-  const int py0 = tob.by * kTileY + (warp >> 1) * 8 + (quarter >> 1) * 4 + 2 * (ql >> 2);
+  const int px = blockIdx.x * kTileX + (warp & 1) * 8 + (quarter & 1) * 4 + (ql & 3);
+  const int py0 = blockIdx.y * kTileY + (warp >> 1) * 8 + (quarter >> 1) * 4 + 2 * (ql >> 2);
   const int py1 = py0 + 1;
   const bool in_a = px < W && py0 < H, in_b = px < W && py1 < H;
   const uint32_t pix_a = (uint32_t)W * (uint32_t)py0 + (uint32_t)px;
   const uint32_t pix_b = pix_a + (uint32_t)W;
   const float pxf = (float)px;
   const f2 npy2 = f2_pack(-(float)py0, -(float)py1);
-  const float tile_x0 = (float)(tob.bx * kTileX), tile_y0 = (float)(tob.by * kTileY);
+  const float tile_x0 = (float)(blockIdx.x * kTileX), tile_y0 = (float)(blockIdx.y * kTileY);
   const int sub0 = 4 * (2 * (warp >> 1)) + 2 * (warp & 1);  // bit of quarter 0 in block_mask16; +1, +4, +5
 
   const uint2 range = ranges[tile];
@@ -513,7 +511,7 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
                             float* out_color, float* out_depth, float* out_median, float* out_alpha,
                             float* out_var, float* gau_unc, int* gau_px, bool debug,
                             cudaStream_t stream) {
-  dim3 grid(cam.grid_x * cam.grid_y, 1, 1);   // CTA -> tile through img.tile_order
+  dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
   // "fwd_packed": 1 = two pixels per lane + quarter-warp lists, 0 = one pixel per lane + half-warp lists,
   // 2 (default) = per variant: packed for -full (C3 0.263 vs 0.295 ms, C4 0.559 vs 0.581), scalar for -light
@@ -521,12 +519,12 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
   // and its stop-before-blending rule on every entry)
   if (options().fwd_packed == 1)
     render_fwdq_kernel<kLight, false, false><<<grid, kFwdQThreads, 0, stream>>>(
-        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, gt_depth, out_color, out_depth,
+        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, out_color, out_depth,
         out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
         img.tile_last, nullptr, FusedLoss{});
   else
   render_fwd_kernel<kLight, false><<<grid, kTileThreads, 0, stream>>>(
-      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, gt_depth, out_color, out_depth,
+      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, out_color, out_depth,
       out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
       img.tile_last, nullptr, FusedLoss{});
   GSR_LAUNCH_OK(debug, stream);
@@ -540,16 +538,16 @@ int launch_render_fwd_light_loss(const Camera& cam, const GeomState& g, const Bi
                                  ImgState& img, const float* bg, float* out_color, float* out_depth,
                                  float* out_median, float* out_alpha, float* out_var,
                                  const FusedLoss& fl, cudaStream_t stream) {
-  dim3 grid(cam.grid_x * cam.grid_y, 1, 1);   // CTA -> tile through img.tile_order
+  dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
   if (options().fwd_packed == 1)
     render_fwdq_kernel<kLight, true, false><<<grid, kFwdQThreads, 0, stream>>>(
-        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, fl.gt_depth, out_color, out_depth,
+        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, fl.gt_depth, out_color, out_depth,
         out_alpha, out_median, out_var, nullptr, nullptr, img.n_contrib, nullptr, nullptr,
         img.tile_last, nullptr, fl);
   else
   render_fwd_kernel<kLight, true><<<grid, kTileThreads, 0, stream>>>(
-      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, fl.gt_depth, out_color, out_depth,
+      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, fl.gt_depth, out_color, out_depth,
       out_alpha, out_median, out_var, nullptr, nullptr, img.n_contrib, nullptr, nullptr,
       img.tile_last, nullptr, fl);
   GSR_LAUNCH_OK(false, stream);
@@ -559,21 +557,21 @@ int launch_render_fwd_light_loss(const Camera& cam, const GeomState& g, const Bi
 int launch_render_fwd_full(const Camera& cam, const GeomState& g, const BinState& b,
                            ImgState& img, const float* bg, float* out_color, float* out_depth,
                            float* out_unc, bool count_related, bool debug, cudaStream_t stream) {
-  dim3 grid(cam.grid_x * cam.grid_y, 1, 1);   // CTA -> tile through img.tile_order
+  dim3 grid(cam.grid_x, cam.grid_y, 1);
   StageScope st(ST_RENDER_FWD, stream);
   if (options().fwd_packed != 0 && count_related)
     render_fwdq_kernel<kFull, false, true><<<grid, kFwdQThreads, 0, stream>>>(
-        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, nullptr, out_color, out_depth,
+        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, nullptr, out_color, out_depth,
         out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,
         img.tile_last, g.counters + 1, FusedLoss{});
   else if (options().fwd_packed != 0)
     render_fwdq_kernel<kFull, false, false><<<grid, kFwdQThreads, 0, stream>>>(
-        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, nullptr, out_color, out_depth,
+        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, nullptr, out_color, out_depth,
         out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,
         img.tile_last, nullptr, FusedLoss{});
   else
   render_fwd_kernel<kFull, false><<<grid, kTileThreads, 0, stream>>>(
-      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, tile_order_arg(img), g.rec, bg, nullptr, out_color, out_depth,
+      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, nullptr, out_color, out_depth,
       out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,
       img.tile_last, count_related ? (g.counters + 1) : nullptr, FusedLoss{});
   GSR_LAUNCH_OK(debug, stream);

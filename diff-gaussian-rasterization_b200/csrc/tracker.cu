@@ -455,7 +455,7 @@ int gsr_tracker_run(gsr_tracker* t, const gsr_track_params* params, int iteratio
     memcpy(key.ptrs, ptrs, sizeof(ptrs));
     key.scale_modifier = t->scale_modifier; key.params = *params;
     key.capacity = t->capacity; key.longest_cap = t->longest_cap;
-    key.opts[0] = options().tight_tiles; key.opts[1] = options().bwd_packed + 16 * cnt_stride() + 256 * (options().tile_lpt != 0) + 512 * options().fwd_packed;
+    key.opts[0] = options().tight_tiles; key.opts[1] = options().bwd_packed + 16 * cnt_stride();
     key.packed = (double)packed_entries >= 1.6 * (double)t->P;
     if (!t->key_valid || memcmp(&key, &t->key, sizeof(key)) != 0 || !t->exec) {
       if (t->exec) { cudaGraphExecDestroy(t->exec); t->exec = nullptr; }

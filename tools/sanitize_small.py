@@ -24,9 +24,6 @@ for variant in ("light", "full"):
             pu.set_option("fwd_packed", fp)
             pu.run_variant(mod, variant, cam, scene, cot)
         pu.set_option("fwd_packed", 2)
-        pu.set_option("tile_lpt", 1)  # tiles handed out longest list first
-        pu.run_variant(mod, variant, cam, scene, cot)
-        pu.set_option("tile_lpt", 0)
         pu.set_option("tile_sort", 0)
         pu.run_variant(mod, variant, cam, scene, cot)
         pu.set_option("tile_sort", 1)
