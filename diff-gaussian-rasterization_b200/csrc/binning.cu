@@ -388,9 +388,9 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, const uint64_t* _
   for (int i = tid; i < n; i += kTileSortThreads) out[i] = (uint32_t)s[i];
 }
 
-// built for 4 CTAs per SM (64 registers, no spills): 0.047 ms at C3 against 0.053 with the compiler's own choice of
-// 80 registers / 3 CTAs (profiles/r02_ab_pre_occ.txt)
-__global__ void __launch_bounds__(kTileSortThreads, 4)
+// built for 6 CTAs per SM (40 registers, no spills): 0.045 ms at C3 against 0.047 at 4 CTAs (64 registers) and 0.053
+// with the compiler's own choice of 80 registers / 3 CTAs (profiles/r02_ab_pre_occ.txt)
+__global__ void __launch_bounds__(kTileSortThreads, 6)
 sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
                   uint32_t* __restrict__ vals, uint32_t capacity, int smem_entries) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];

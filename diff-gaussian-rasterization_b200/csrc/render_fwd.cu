@@ -253,7 +253,7 @@ constexpr int kFwdQWarps = kFwdQThreads / 32;
 constexpr int kFwdQBatch = 128;
 
 template <int VARIANT, bool LOSS, bool COUNT>
-__global__ void __launch_bounds__(kFwdQThreads, 8)
+__global__ void __launch_bounds__(kFwdQThreads, 8)   // (7 CTAs per SM / 71 registers measured equal: 0.263 vs 0.265 ms)
 render_fwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                    int W, int H, int grid_x, const float4* __restrict__ rec,
                    const float* __restrict__ bg, const float* __restrict__ gt_depth,

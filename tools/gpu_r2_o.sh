@@ -1,0 +1,5 @@
+#!/usr/bin/env bash
+# round 2: A/B of compile-time variants (option tune: bit 0 = sort 6 CTAs/SM, bit 1 = -full forward blend 7 CTAs/SM)
+set -u
+O=gpurun_out/r2o; mkdir -p $O
+bash tools/gpu_ab_opts.sh "C3 full;C4 full" "tune=0" "tune=1" "tune=2" 2>&1 | tee $O/ab_tune.txt
