@@ -127,7 +127,9 @@ def stage_bytes(stage, P, N, HW, tiles, M, variant, sort_bits, tile_local=True):
         "preprocess_fwd": (44 + 12 * M) * P + 75 * P,
         "render_fwd": 44 * N + HW * (4 + 4 * c_out + 8),
         "render_bwd": 44 * N + HW * (4 * c_grad + 12) + 48 * P,
-        "preprocess_bwd": (359 + 44 + 12 * M) * P,
+        # SURVEY 8d's 359 + 44 + 12 M bytes minus the 56 bytes per Gaussian of gradients nobody reads, which the
+        # kernel no longer writes (dL/dconic 16, dL/ddepth 4, dL/dcolors_precomp 12, dL/dcov3D_precomp 24)
+        "preprocess_bwd": (303 + 44 + 12 * M) * P,
     }
     if tile_local:
         table.update({"scan": 16 * tiles, "emit_keys": 28 * P + 12 * N, "radix_sort": 12 * N})

@@ -417,8 +417,9 @@ int gsr_light_forward(
   };
   rc = forward_front(a, kLight, cam, g, b, img, num_rendered, &spec);
   if (rc != GSR_OK) return rc;
-  if (spec.done) return GSR_OK;
-  return spec.launch(b);
+  if (!spec.done) rc = spec.launch(b);
+  if (acc_begun) acc_clear_rejoin(g.rec, s);
+  return rc;
 }
 
 int gsr_full_forward(
@@ -470,6 +471,7 @@ int gsr_full_forward(
     rc = spec.launch(b);
     if (rc != GSR_OK) return rc;
   }
+  if (acc_begun) acc_clear_rejoin(g.rec, s);
   if (count) {
     uint32_t ng = 0;
     GSR_CUDA_OK(cudaMemcpyAsync(&ng, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

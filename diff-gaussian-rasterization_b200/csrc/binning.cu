@@ -601,6 +601,17 @@ void acc_clear_begin(const void* geom_key, void* acc, size_t bytes, cudaStream_t
   a->key[i] = geom_key; a->pending[i] = true;
 }
 
+void acc_clear_rejoin(const void* geom_key, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  AccClear* a = acc_clear_state();
+  if (a == nullptr) return;
+  for (int k = 0; k < AccClear::kRing; ++k)
+    if (a->key[k] == geom_key && a->pending[k]) {
+      if (cudaStreamWaitEvent(stream, a->done[k], 0) != cudaSuccess) cudaGetLastError();
+      return;
+    }
+}
+
 bool acc_clear_join(const void* geom_key, cudaStream_t stream) {
   std::lock_guard<std::mutex> lk(g_ctx_mu);
   AccClear* a = acc_clear_state();

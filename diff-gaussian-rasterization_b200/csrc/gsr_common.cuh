@@ -181,6 +181,10 @@ struct ImgState {
 // overrun, option off), clears its scratch itself as before.
 void acc_clear_begin(const void* geom_key, void* acc, size_t bytes, cudaStream_t stream);
 bool acc_clear_join(const void* geom_key, cudaStream_t stream);
+// End of the forward: everything enqueued on `stream` from here on is ordered after the pending clear of this
+// buffer (it has long finished by then — the point is that the caller's allocator, which only knows `stream`,
+// may hand the geometry buffer's memory to somebody else if the caller drops it without running a backward).
+void acc_clear_rejoin(const void* geom_key, cudaStream_t stream);
 
 size_t scan_temp_bytes(int P);
 size_t sort_temp_bytes(size_t N, int end_bit);
