@@ -163,6 +163,7 @@ scan_tiles_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __r
   __shared__ uint32_t s_carry, s_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto slot = [](int i) { return i + (i >> 3); };
+  pdl_wait();   // (launched programmatically behind preprocess_fwd, whose counters it scans)
   if (tid == 0) { s_carry = 0; s_max = 0; }
   uint32_t local_max = 0;
   for (int base = 0; base < tiles; base += 1024 * kScanPer) {
@@ -251,6 +252,7 @@ __global__ void scatter_entries_kernel(int P, const float4* __restrict__ rec,
   // `capacity` = entries the buffer can hold.  It only bites when the buffer was sized from the
   // previous frame's count (speculative launch, see run_binning) and this frame has more: the
   // surplus is dropped and the host, which sees the real count, redoes the binning.
+  pdl_trigger();   // the per-tile sort behind this kernel may be set up while it runs
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t n = (idx < P) ? tiles_touched[idx] : 0u;
@@ -395,6 +397,8 @@ sort_tiles_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__
                   uint32_t* __restrict__ vals, uint32_t capacity, int smem_entries) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
   uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem_raw);
+  pdl_wait();      // launched programmatically behind the scatter
+  pdl_trigger();   // ... and the forward blend behind this kernel
   const uint2 range = ranges[blockIdx.x];
   const int n = (int)(range.y - range.x);
   if (n == 0) return;
@@ -571,7 +575,8 @@ int launch_tile_sort(const Camera& cam, int P, const GeomState& g, const ImgStat
                                        kTileSortCap * (int)sizeof(uint64_t)));
       if (ds != nullptr) ds->sort_attr_set = true;
     }
-    sort_tiles_kernel<<<tiles, kTileSortThreads, smem, stream>>>(img.ranges, b.keys_unsorted, b.vals, capacity, p);
+    launch_after(options().pdl != 0, sort_tiles_kernel, dim3(tiles), dim3(kTileSortThreads), smem, stream,
+                 (const uint2*)img.ranges, (const uint64_t*)b.keys_unsorted, b.vals, capacity, p);
     GSR_LAUNCH_OK(debug, stream);
   }
   return GSR_OK;
@@ -683,9 +688,9 @@ int run_binning(int P, const Camera& cam, const int* /*radii*/, GeomState& g, gs
     {
       // img.tile_count was filled by preprocess_fwd (one red per duplicate)
       StageScope st(ST_SCAN, stream, 1);
-      scan_tiles_kernel<<<1, 1024, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_fill, g.counters,
-                                                speculate ? cap : 0xFFFFFFFFu, speculate ? lpad : 0xFFFFFFFFu,
-                                                cnt_stride(), true);
+      launch_after(options().pdl != 0, scan_tiles_kernel, dim3(1), dim3(1024), 0, stream, tiles,
+                   (const uint32_t*)img.tile_count, img.ranges, img.tile_fill, g.counters,
+                   speculate ? cap : 0xFFFFFFFFu, speculate ? lpad : 0xFFFFFFFFu, cnt_stride(), true);
       GSR_LAUNCH_OK(debug, stream);
     }
     uint32_t h[4] = {0, 0, 0, 0};

@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <functional>
+#include <cstring>
 #include <stdint.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -57,6 +58,7 @@ struct Options {
   int fwd_packed;
   int spec_render;   // 1: forward blend enqueued before the host waits for the duplicate count
   int early_acc_clear;  // 1: the forward clears the backward's accumulator on a side stream (acc_clear_begin)
+  int pdl;              // 1: dependent kernels of a frame are launched programmatically (launch_after)
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the
@@ -174,6 +176,35 @@ struct ImgState {
   uint32_t* tile_fill;      // [tiles] scatter cursor per tile
   static size_t carve(ImgState& s, char* base, int HW, int tiles, int variant);
 };
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// A kernel launched with launch_after(true, ...) right behind another kernel on the same stream may be set up —
+// and its CTAs scheduled onto free SM slots — while the tail of that kernel is still running; its first statement
+// is pdl_wait(), which returns once the preceding kernel has completed and its writes are visible.  The preceding
+// kernel calls pdl_trigger() at its start (it fires when every one of its CTAs has been scheduled).  Hides the
+// launch latency between the frame's dependent kernels (nine launches of 4-5 us around kernels of 10-100 us on
+// the small frames).  Both instructions are no-ops for kernels that were launched the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_after(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                         Args... args) {
+  if (!pdl) {
+    kernel<<<grid, block, smem, s>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);   // (errors are picked up by GSR_LAUNCH_OK's cudaGetLastError)
+}
+#endif
+
 // Accumulator clear moved out of the backward's critical path: the forward enqueues the memset of GeomState::acc on
 // a library-owned side stream (ordered after everything already on `stream`, i.e. after the previous frame), where
 // it runs underneath the forward's kernels; the backward of the same geometry buffer makes its stream wait for it

@@ -63,6 +63,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   extern __shared__ __align__(16) float sh_smem[];  // [kBwdThreads][row] SH in, dL/dSH out
   __shared__ float s_pose[kBwdThreads / 32][12];
   __shared__ uint64_t s_bar;
+  pdl_wait();   // (may have been launched programmatically behind the blend backward)
   const int base = blockIdx.x * kBwdThreads;
   const int idx = base + threadIdx.x;
   constexpr int kBulkRow = bulk_row_floats(MT * 3);
@@ -607,10 +608,11 @@ int launch_preprocess_bwd(int variant, int P, int D, int M, const float* means3D
   {
 #define GSR_PRE_BWD(V, MT, TMA)                                                                  \
   prefer_max_shared_once(reinterpret_cast<const void*>(&preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1>)); \
-  preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1><<<blocks, kBwdThreads, smem, stream>>>( \
-      P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
-      cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, acc,  \
-      g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr, done_counter)
+  launch_after(options().pdl != 0, preprocess_bwd_kernel<V, MT, TMA, ((MT) == 16 && (TMA)) ? 5 : 1>,   \
+      dim3(blocks), dim3(kBwdThreads), smem, stream,                                             \
+      P, D, M, means3D, (const int*)radii, shs, (const unsigned char*)g.clamped, scales, rotations, scale_modifier, cov3D, cam.view, \
+      cam.proj, cam.campos, perspec, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, (const float*)acc,  \
+      (const float4*)g.rec, cam.W, cam.H, pose_partials, out, want_gauss, want_pose, nullptr, done_counter)
 #define GSR_PRE_BWD_M(V)                                                                         \
   if (tma) {   /* 5 CTAs per SM (96 registers); the 6-CTA build (80 registers, 72 bytes spilled) measured equal */ \
     if (M == 16) { GSR_PRE_BWD(V, 16, true); } else { GSR_PRE_BWD(V, 4, true); }                 \

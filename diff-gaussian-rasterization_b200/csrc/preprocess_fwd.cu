@@ -198,6 +198,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   //               evaluated.
   extern __shared__ __align__(16) float sh_smem[];
   __shared__ uint64_t s_bar;
+  pdl_trigger();   // the tile scan behind this kernel may be set up while it runs
   const int base = blockIdx.x * kPreThreads;
   const int idx = base + threadIdx.x;
   constexpr int kBulkRow = bulk_row_floats(MT * 3);

@@ -577,6 +577,7 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   __shared__ __align__(16) unsigned char s_list[kBwdQWarps][kBwdQBatch][4];
   __shared__ __align__(16) float s_red[kRedVals][red_row(kBwdQWarps)];
 
+  pdl_trigger();   // the per-Gaussian backward kernel behind this one may be set up while it runs
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int quarter = lane >> 3, ql = lane & 7;

@@ -44,6 +44,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ uint32_t s_red[kTileThreads / 32];
   __shared__ float s_loss[kTileThreads / 32];
 
+  pdl_wait();   // (may have been launched programmatically behind the per-tile sort)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.y * grid_x + blockIdx.x;
@@ -272,6 +273,7 @@ render_fwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
   __shared__ uint32_t s_red[kFwdQWarps];
   __shared__ float s_loss[kFwdQWarps];
 
+  pdl_wait();   // (may have been launched programmatically behind the per-tile sort)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int quarter = lane >> 3, ql = lane & 7;
@@ -523,8 +525,8 @@ int launch_render_fwd_light(const Camera& cam, const GeomState& g, const BinStat
         out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
         img.tile_last, nullptr, FusedLoss{});
   else
-  render_fwd_kernel<kLight, false><<<grid, kTileThreads, 0, stream>>>(
-      img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, gt_depth, out_color, out_depth,
+  launch_after(options().pdl != 0, render_fwd_kernel<kLight, false>, grid, dim3(kTileThreads), 0, stream,
+      (const uint2*)img.ranges, (const uint32_t*)b.vals, cam.W, cam.H, cam.grid_x, (const float4*)g.rec, bg, gt_depth, out_color, out_depth,
       out_alpha, out_median, out_var, gau_unc, gau_px, img.n_contrib, nullptr, nullptr,
       img.tile_last, nullptr, FusedLoss{});
   GSR_LAUNCH_OK(debug, stream);
@@ -565,8 +567,8 @@ int launch_render_fwd_full(const Camera& cam, const GeomState& g, const BinState
         out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,
         img.tile_last, g.counters + 1, FusedLoss{});
   else if (options().fwd_packed != 0)
-    render_fwdq_kernel<kFull, false, false><<<grid, kFwdQThreads, 0, stream>>>(
-        img.ranges, b.vals, cam.W, cam.H, cam.grid_x, g.rec, bg, nullptr, out_color, out_depth,
+    launch_after(options().pdl != 0, render_fwdq_kernel<kFull, false, false>, grid, dim3(kFwdQThreads), 0, stream,
+        (const uint2*)img.ranges, (const uint32_t*)b.vals, cam.W, cam.H, cam.grid_x, (const float4*)g.rec, bg, nullptr, out_color, out_depth,
         out_unc, nullptr, nullptr, nullptr, nullptr, img.n_contrib, img.final_T, img.first_contrib,
         img.tile_last, nullptr, FusedLoss{});
   else

@@ -86,6 +86,10 @@ def main():
         f.write("".join(open(os.path.join(SRC, "pytest_gpu.log"), errors="replace").readlines()[-6:]))
         f.write("\n# python -c 'import __graft_entry__ as g; g.smoke()'\n")
         f.write("".join(open(os.path.join(SRC, "smoke.log"), errors="replace").readlines()[-6:]))
+    for seed in (2, 3):
+        fn = os.path.join(SRC, "parity_fuzz_1500_seed%d.txt" % seed)
+        if os.path.exists(fn):
+            shutil.copy(fn, os.path.join(DST, "r02_parity_fuzz_1500_seed%d_%s.txt" % (seed, tag)))
     with open(os.path.join(DST, "r02_sanitizers_%s.txt" % tag), "w") as f:
         f.write("# compute-sanitizer --tool <tool> python tools/sanitize_small.py  (both variants, every blend-kernel variant,\n"
                 "# radix + tile-local binning, a speculative frame that overflows and is redone, the exchange helpers, the loss\n"

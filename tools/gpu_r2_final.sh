@@ -34,6 +34,10 @@ for tool in memcheck racecheck; do
 done
 GSR_SANITIZE_SMALL=1 GSR_TEST_OPTS=bulk_sh=0 timeout 600 compute-sanitizer --tool initcheck --print-limit 5 python tools/sanitize_small.py > $O/sanitize_initcheck.txt 2>&1
 echo "exit $?" >> $O/sanitize_initcheck.txt
+for seed in 2 3; do
+  timeout 900 python tools/parity_fuzz.py --cases 1500 --seed $seed --out $O/parity_fuzz_1500_seed$seed.txt > /dev/null 2>>$O/parity_fuzz.err; echo "fuzz seed $seed exit $?"
+  tail -n 1 $O/parity_fuzz_1500_seed$seed.txt | cut -c1-300
+done
 tail -n 4 $O/sanitize_*.txt
 cat $O/configs.txt | tail -8
 ls -la $O | head -50

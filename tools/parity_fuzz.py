@@ -41,7 +41,7 @@ def main():
         W, H = int(rng.randint(17, 420)), int(rng.randint(17, 300))
         if rng.rand() < 0.3:
             W, H = 16 * (W // 16 + 1), 16 * (H // 16 + 1)
-        P = int(rng.choice([1, 7, 60, 500, 3000, 12000, 40000]))
+        P = int(rng.choice([1, 7, 60, 500, 3000, 12000, 40000, 150000]))
         lo = float(rng.choice([0.3, 1.0, 2.0])); hi = lo * float(rng.choice([2.0, 6.0, 15.0]))
         backdrop = bool(rng.rand() < 0.4) and P > 2 * max(2, W // 24) * max(2, H // 24)   # the backdrop grid is part of P
         deg = int(rng.randint(0, 4))
