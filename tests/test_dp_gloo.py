@@ -85,7 +85,7 @@ def _worker_fact(rank, world, port, P, M, q, mode="factorized_sh"):
     grads, dR, campos = rank_data(rank)
     red = dp.SceneGradReducer(shapes, "cpu", mode=mode, means3D=means, sh_degree=3)
     assert red.numel == 14 * P + 4
-    if mode == "nvls":  # no CUDA / no NVSwitch here: the reducer must say so and use the NCCL-style exchange
+    if mode in ("nvls", "p2p"):  # no CUDA / no NVSwitch here: the reducer must say so and use the NCCL-style exchange
         assert red.mode == "factorized_sh" and red.nvls is None and "nvls unavailable" in red.nvls_note
     red.reduce_async(grads, masked_color=dR, campos=campos)
     views = red.wait()
@@ -119,12 +119,13 @@ def test_factorized_sh_exchange_world2():
     assert all(ok for _, ok in res)
 
 
-def test_nvls_mode_falls_back_to_factorized_exchange_without_multicast():
+@pytest.mark.parametrize("mode", ["nvls", "p2p"])
+def test_nvls_mode_falls_back_to_factorized_exchange_without_multicast(mode):
     world, P, M = 2, 64, 16
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_fact, args=(r, world, port, P, M, q, "nvls")) for r in range(world)]
+    procs = [ctx.Process(target=_worker_fact, args=(r, world, port, P, M, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))

@@ -71,3 +71,34 @@ def test_nvls_kernels_use_sys_scope_multimem_operations(built):
     # multimem.ld_reduce -> LDGMC (load with in-switch reduction), multimem.st -> sys-scope STG.128
     assert _count(sh, r"LDGMC\.E\.ADD\.F32x4") >= 1, "no multimem.ld_reduce in sh_grad_views.o"
     assert _count(sh, r"STG\.E\.128\.STRONG\.SYS") >= 1
+
+
+def test_p2p_exchange_kernels_use_sys_scope_128_bit_accesses(built):
+    """The two-shot slice all-reduce and the gather read / write the peers' replicas with 128-bit sys-scope
+    loads and stores (ld / st.relaxed.sys.v4)."""
+    sh = _sass("sh_grad_views.o")
+    assert _count(sh, r"LDG\.E\.128\.STRONG\.SYS") >= 8 and _count(sh, r"STG\.E\.128\.STRONG\.SYS") >= 8
+
+
+def test_frame_kernels_are_chained_by_programmatic_dependent_launch(built):
+    """griddepcontrol.wait -> ACQBULK at the top of the dependent kernels (tile scan, per-tile sort, forward blend,
+    per-Gaussian backward), griddepcontrol.launch_dependents -> PREEXIT in the kernels in front of them."""
+    waits = {o: _count(_sass(o), r"\bACQBULK\b") for o in ("binning.o", "render_fwd.o", "preprocess_bwd.o")}
+    triggers = {o: _count(_sass(o), r"\bPREEXIT\b") for o in ("preprocess_fwd.o", "binning.o", "render_bwd.o")}
+    assert all(v >= 1 for v in waits.values()), waits
+    assert all(v >= 1 for v in triggers.values()), triggers
+
+
+def test_backward_blend_and_sort_register_budgets(built):
+    """The default (quarter-list) backward blend kernels fit 7 CTAs of 128 threads per SM (<= 72 registers, no
+    spills); the per-tile sort fits 6 CTAs of 256 threads (<= 40 registers, no spills)."""
+    out = subprocess.run([CUOBJDUMP, "-res-usage", os.path.join(OBJ, "render_bwd.o")], capture_output=True, text=True).stdout
+    rows = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    q7 = [(n, int(r), int(st)) for n, r, st in rows if re.search(r"render_bwdq_kernelILi[01]ELb[01]ELi7", n)]
+    assert len(q7) >= 3
+    for n, r, st in q7:
+        assert r <= 72 and st == 0, (n, r, st)
+    out = subprocess.run([CUOBJDUMP, "-res-usage", os.path.join(OBJ, "binning.o")], capture_output=True, text=True).stdout
+    rows = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    srt = [(n, int(r), int(st)) for n, r, st in rows if "sort_tiles_kernel" in n]
+    assert srt and all(r <= 40 and st == 0 for _, r, st in srt), srt
