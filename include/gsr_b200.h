@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GSR_B200_ABI_VERSION 4
+#define GSR_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define GSR_API __attribute__((visibility("default")))

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(built.core_library_path())
     for s in declared_symbols():
         assert hasattr(lib, s), "libgsr_b200.so does not export %s" % s
-    assert lib.gsr_abi_version() == 4
+    assert lib.gsr_abi_version() == 5
 
 
 def test_scratch_size_and_options(built):
