@@ -24,7 +24,7 @@ std::atomic<long long> g_launches{0};
 // when it starts (OptionsCall), and everything below reads the snapshot: a concurrent
 // gsr_set_option from another thread can never change the switches in the middle of a call, and a
 // value one thread's call is using is never written by another thread.
-Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1, /*early_acc_clear=*/1, /*pdl=*/1};
+Options g_opts = {/*exact_ng=*/0, /*tight_tiles=*/1, /*stage_timing=*/0, /*tile_sort=*/1, /*bwd_packed=*/2, /*async_binning=*/1, /*track_headroom_pct=*/50, /*bulk_sh=*/1, /*cnt_stride=*/8, /*bwd_occ=*/0, /*fwd_packed=*/2, /*spec_render=*/1, /*early_acc_clear=*/1, /*pdl=*/1, /*exact_median=*/0};
 
 // Stage timer: a pool of event pairs filled by StageScope and drained by gsr_stage_times().
 struct StageTimer {
@@ -328,6 +328,7 @@ static int* option_slot(const char* key) {
   if (!strcmp(key, "spec_render")) return &g_opts.spec_render;
   if (!strcmp(key, "early_acc_clear")) return &g_opts.early_acc_clear;
   if (!strcmp(key, "pdl")) return &g_opts.pdl;
+  if (!strcmp(key, "exact_median")) return &g_opts.exact_median;
   return nullptr;
 }
 

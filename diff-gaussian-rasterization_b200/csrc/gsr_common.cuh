@@ -59,6 +59,7 @@ struct Options {
   int spec_render;   // 1: forward blend enqueued before the host waits for the duplicate count
   int early_acc_clear;  // 1: the forward clears the backward's accumulator on a side stream (acc_clear_begin)
   int pdl;              // 1: dependent kernels of a frame are launched programmatically (launch_after)
+  int exact_median;     // 1: -light backward restores T with the reference's exact arithmetic (render_bwdq_kernel<..., EXACT>)
 };
 Options& options();  // the calling thread's snapshot (see OptionsCall)
 // RAII at the top of every extern "C" entry point: copies the process-wide option defaults into the

@@ -553,7 +553,11 @@ __device__ __forceinline__ float row8_sum(unsigned addr) {
   return f2_lo(t) + f2_hi(t);
 }
 
-template <int VARIANT, bool POSE_ONLY, int MINB>
+// EXACT (option "exact_median", -light only): exp(power) with expf and T restored with an IEEE division, i.e. the
+// reference's own arithmetic for the chain that decides which entry receives the median-depth gradient
+// (DESIGN.md section 2): the 2-in-3000 random cases where the approximate chain sends that gradient to the
+// neighbouring entry disappear, at ~13 % more instructions per iteration.
+template <int VARIANT, bool POSE_ONLY, int MINB, bool EXACT = false>
 __global__ void __launch_bounds__(kBwdQThreads, MINB)
 render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                    const uint32_t* __restrict__ tile_last, int W, int H, int grid_x,
@@ -701,11 +705,14 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       bool vb = active && (pos < lc_b) && !(pw_b > 0.0f) && !(pw_b < pc);
       if (!__any_sync(0xffffffffu, va || vb)) continue;
       const float o = f2_lo(e2.y), ps = f2_hi(e2.y);
-      float Ga = fast_exp(pw_a), Gb = fast_exp(pw_b);
+      float Ga = EXACT ? expf(pw_a) : fast_exp(pw_a), Gb = EXACT ? expf(pw_b) : fast_exp(pw_b);
       float al_a = pair_alpha(o, Ga), al_b = pair_alpha(o, Gb);
       // the forward blended this pair iff min(0.99, o * expf(power)) >= 15/255: certain for power >=
       // power_sure; the few pairs below it repeat the forward's exact evaluation (divergent, rare)
-      if ((va && pw_a < ps) || (vb && pw_b < ps)) {
+      if (EXACT) {
+        va = va && !(al_a < kAlphaMin);
+        vb = vb && !(al_b < kAlphaMin);
+      } else if ((va && pw_a < ps) || (vb && pw_b < ps)) {
         if (va && pw_a < ps) { Ga = expf(pw_a); al_a = pair_alpha(o, Ga); va = !(al_a < kAlphaMin); }
         if (vb && pw_b < ps) { Gb = expf(pw_b); al_b = pair_alpha(o, Gb); vb = !(al_b < kAlphaMin); }
       }
@@ -718,7 +725,8 @@ render_bwdq_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict_
       const ulonglong2 e3 = eq[3 * kBwdQBatch], e4 = eq[4 * kBwdQBatch];
       const f2 om2 = f2_fma(alpha2, mone2, one2);  // 1 - alpha (>= 0.01)
       const f2 inv2 = f2_pack(fast_rcp(f2_lo(om2)), fast_rcp(f2_hi(om2)));
-      T2 = f2_mul(T2, inv2);
+      if (EXACT) T2 = f2_pack(__fdiv_rn(f2_lo(T2), f2_lo(om2)), __fdiv_rn(f2_hi(T2), f2_hi(om2)));   // as the reference: T / (1 - alpha)
+      else T2 = f2_mul(T2, inv2);
       const f2 aT2 = f2_mul(alpha2, T2);
       // c - B for colour, depth and var
       const f2 d0 = f2_fma(Bc0, mone2, e3.y), d1 = f2_fma(Bc1, mone2, e4.x), d2 = f2_fma(Bc2, mone2, e4.y);
@@ -1131,7 +1139,9 @@ int launch_render_bwd(int variant, const Camera& cam, const GeomState& g, const 
       img.n_contrib, FC, cot.dL_dpix, cot.dL_ddepth, cot.dL_dmedian, cot.dL_dvar, acc
 #define GSR_BWDQ(V, PO, FT, FC)                                                                    \
   do {                                                                                             \
-    if (occ7) render_bwdq_kernel<V, PO, 7><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC)); \
+    if (V == kLight && !PO && options().exact_median != 0)                                         \
+      render_bwdq_kernel<kLight, false, 7, true><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC)); \
+    else if (occ7) render_bwdq_kernel<V, PO, 7><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC)); \
     else render_bwdq_kernel<V, PO, 8><<<grid, kBwdQThreads, 0, stream>>>(GSR_BWD_ARGS(FT, FC));    \
   } while (0)
   const dim3 grid_o(2 * cam.grid_x, cam.grid_y, 1);   // octet kernel: one warp per half tile

@@ -18,7 +18,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=120); ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (gsr_set_option)")
     a = ap.parse_args()
+    for kv in a.opt:
+        k, v = kv.split("=")
+        assert pu.set_option(k, int(v)) >= 0, "unknown option " + k
     rng = np.random.RandomState(a.seed)
     sc = ge.load_scene_module()
     import importlib.util
@@ -33,7 +37,7 @@ def main():
         print(s, flush=True)
         if log:
             log.write(s + "\n"); log.flush()
-    say("# tools/parity_fuzz.py --cases %d --seed %d   (%s, %s)" % (a.cases, a.seed, torch.cuda.get_device_name(0), time.strftime("%Y-%m-%d %H:%M:%S")))
+    say("# tools/parity_fuzz.py --cases %d --seed %d %s  (%s, %s)" % (a.cases, a.seed, " ".join("--opt " + o for o in a.opt), torch.cuda.get_device_name(0), time.strftime("%Y-%m-%d %H:%M:%S")))
     worst = dict(pixels_over=0, int_mismatches=0, grad_max_rel=0.0, fwd_max_abs=0.0)
     failed = 0
     for case in range(a.cases):
