@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# (historical record of a round-2 GPU call: the A/B option it toggles was removed after the measurement, see profiles/r02_ab_*.txt)
 # round 2, call 11: tiles handed out longest list first (tile_lpt): full GPU suite + A/B
 set -u
 O=gpurun_out/r2k; mkdir -p $O

@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# (historical record of a round-2 GPU call: the A/B option it toggles was removed after the measurement, see profiles/r02_ab_*.txt)
 # round 2: full GPU suite after the clean-up, the tracker convergence test repeated (flaky?), bench
 set -u
 O=gpurun_out/r2n; mkdir -p $O
